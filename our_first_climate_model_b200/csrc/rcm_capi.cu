@@ -1,0 +1,638 @@
+// C ABI of the solver (include/rcm_b200.h): handle management, host-side precomputation of
+// everything that depends only on the shared pressure grid / wavelength table, uploads,
+// launches and downloads.  No CPU fallback: without a CUDA device rcm_create() fails.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "rcm_kernels.cuh"
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+struct rcm_solver {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    rcm_params p{};
+    DevConst dc{};
+    bool const_dirty = true;
+    int opt_angle_cubes = 1;
+    // table
+    bool has_table = false;
+    std::vector<double> p_grid, t_ref, t_pert, wvl, weight;
+    double *d_xsec = nullptr, *d_planck_c = nullptr, *d_planck_k = nullptr, *d_exp_tab = nullptr;
+    // columns
+    int ncol = 0, cap = 0, nactive = 0, h2o_slot = -1;
+    int species[RCM_NSPECIES]{};
+    bool has_plevel = false;
+    double plevel[RCM_NLEVEL]{};
+    double *d_T = nullptr, *d_Ts = nullptr, *d_vmr = nullptr, *d_rh = nullptr, *d_Tprev = nullptr;
+    float* d_time = nullptr;
+    double *d_Ed = nullptr, *d_Eu = nullptr, *d_dE = nullptr, *d_dt = nullptr;
+    double *d_diag = nullptr, *d_scalars = nullptr, *d_tau = nullptr;
+    int* d_lowpos = nullptr;
+    size_t diag_steps = 0, tau_cap = 0;
+    long step_index = 0;
+    bool tau_valid = false;
+    std::vector<double> stage;  // host packing buffer
+    std::string err;
+    long launches = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_free, ev_used;
+    double kt_ms = 0.0;
+    long kt_n = 0;
+};
+
+namespace {
+
+int fail(rcm_solver* s, int code, const std::string& msg) {
+    if (s) s->err = msg;
+    return code;
+}
+
+int cuda_fail(rcm_solver* s, cudaError_t e, const char* what) {
+    return fail(s, RCM_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define CU(call)                                          \
+    do {                                                  \
+        cudaError_t e__ = (call);                         \
+        if (e__ != cudaSuccess) return cuda_fail(s, e__, #call); \
+    } while (0)
+
+template <class T>
+cudaError_t dalloc(T*& p, size_t n) {
+    if (p) cudaFree(p);
+    p = nullptr;
+    return cudaMalloc((void**)&p, n * sizeof(T));
+}
+
+void set_active_species(rcm_solver* s) {
+    s->nactive = 0;
+    s->h2o_slot = -1;
+    for (int k = 0; k < RCM_NSPECIES; ++k)
+        if (s->p.species_mask & (1u << k)) {
+            if (k == 0) s->h2o_slot = s->nactive;
+            s->species[s->nactive++] = k;
+        }
+}
+
+// Angle schedule.  Quadrature nodes mu_i = dmu/2 + dmu*i (main.cpp:482) = (2i+1)/(2*nangle).  With
+// n = 2i+1, 1/mu is proportional to 1/n, hence t(n/3) = t(n)^3: nodes are visited in chains
+// n, n/3, n/9, ... so that only the chain heads need an exp.  Summation order over angles
+// changes, values of mu do not.
+void build_angles(rcm_solver* s) {
+    DevConst& d = s->dc;
+    const int na = s->p.nangle;
+    const double dmu = 1.0 / (double)na;
+    d.nangle = na;
+    std::vector<int> order;
+    std::vector<int> cube;
+    if (s->opt_angle_cubes) {
+        std::vector<char> used(na, 0);
+        for (int i = na - 1; i >= 0; --i) {
+            if (used[i]) continue;
+            int n = 2 * i + 1;
+            bool head = true;
+            while (true) {
+                const int idx = (n - 1) / 2;
+                used[idx] = 1;
+                order.push_back(idx);
+                cube.push_back(head ? 0 : 1);
+                head = false;
+                if (n % 3 != 0) break;
+                n /= 3;
+            }
+        }
+    } else {
+        for (int i = 0; i < na; ++i) {
+            order.push_back(i);
+            cube.push_back(0);
+        }
+    }
+    double sum = 0.0;
+    for (int a = 0; a < na; ++a) {
+        const double mu = dmu / 2.0 + dmu * (double)order[a];
+        d.neg_inv_mu[a] = -1.0 / mu;
+        d.cmu[a] = 2 * M_PI * mu * dmu;
+        d.cube[a] = cube[a];
+        sum += d.cmu[a];
+    }
+    d.csum = sum;
+}
+
+int refresh_const(rcm_solver* s) {
+    if (!s->const_dirty) return RCM_OK;
+    DevConst& d = s->dc;
+    set_active_species(s);
+    d.nactive = s->nactive;
+    for (int k = 0; k < RCM_NSPECIES; ++k) d.species[k] = (k < s->nactive) ? s->species[k] : 0;
+    d.cloud_layer = s->p.cloud_layer;
+    d.cloud_tau = s->p.cloud_tau;
+    d.dp = s->p.dp;
+    d.max_dT = s->p.max_dT;
+    d.dt_cap = s->p.dt_cap;
+    d.solar_irr = s->p.solar_irr;
+    d.dT_converged = s->p.dT_converged;
+    build_angles(s);
+    if (s->has_table && s->has_plevel) {
+        // per-layer quantities of the shared pressure grid, reference expressions
+        // (repwvl_thermal.cpp:72, :89, :202, :214, :226, :240), bottom-up index k = 19 - l
+        const double avog = 6.02214076e23, molMassAir = 0.0289647, earthAccel = 9.80665;
+        double P[RCM_NLEVEL];
+        for (int k = 0; k < RCM_NLEVEL; ++k) P[k] = s->plevel[RCM_NLEVEL - 1 - k] * 100.0;
+        for (int k = 0; k < RCM_NLAYER; ++k) {
+            const int l = RCM_NLAYER - 1 - k;
+            const double midP = (P[k + 1] + P[k]) / 2;
+            const long ip = rcm_lowerpos_impl(s->p_grid.data(), (int)s->p_grid.size(), midP);
+            d.ip[l] = (int)ip;
+            d.delP[l] = (midP - s->p_grid[ip]) / (s->p_grid[ip + 1] - s->p_grid[ip]);
+            d.numDens[l] = (P[k] - P[k + 1]) * avog / molMassAir / earthAccel;
+            d.tref_ip[l] = s->t_ref[ip];
+        }
+    }
+    if (s->has_plevel) {
+        for (int l = 0; l < RCM_NLAYER; ++l) {
+            d.player[l] = (s->plevel[l] + s->plevel[l + 1]) / 2.0;     // main.cpp:472
+            d.conv[l] = std::pow(1000.0 / d.player[l], 2.0 / 7.0);     // main.cpp:474
+        }
+    }
+    cudaError_t e = rcm_upload_const(d);
+    if (e != cudaSuccess) return cuda_fail(s, e, "upload constants");
+    s->const_dirty = false;
+    return RCM_OK;
+}
+
+int ensure_columns(rcm_solver* s, int ncol) {
+    if (ncol <= s->cap && s->d_T) return RCM_OK;
+    const size_t n = (size_t)ncol;
+    CU(dalloc(s->d_T, n * NLAY));
+    CU(dalloc(s->d_Ts, n));
+    CU(dalloc(s->d_vmr, n * RCM_NSPECIES * NLAY));
+    CU(dalloc(s->d_rh, n * NLAY));
+    CU(dalloc(s->d_Tprev, n * NLAY));
+    CU(dalloc(s->d_time, n));
+    CU(dalloc(s->d_Ed, n * NLEV));
+    CU(dalloc(s->d_Eu, n * NLEV));
+    CU(dalloc(s->d_dE, n * NLAY));
+    CU(dalloc(s->d_dt, n));
+    CU(dalloc(s->d_lowpos, n * NLAY));
+    s->cap = ncol;
+    s->diag_steps = 0;
+    return RCM_OK;
+}
+
+int ensure_diag(rcm_solver* s, int nsteps) {
+    if ((size_t)nsteps <= s->diag_steps && s->d_diag) return RCM_OK;
+    CU(dalloc(s->d_diag, (size_t)nsteps * s->cap * 4));
+    CU(dalloc(s->d_scalars, (size_t)nsteps * 4));
+    s->diag_steps = nsteps;
+    return RCM_OK;
+}
+
+int ensure_tau(rcm_solver* s) {
+    const size_t need = (size_t)s->ncol * s->dc.nwvl * NLAY;
+    if (need <= s->tau_cap && s->d_tau) return RCM_OK;
+    CU(dalloc(s->d_tau, need));
+    s->tau_cap = need;
+    return RCM_OK;
+}
+
+// Columns per tile: 64 when the ensemble fills the GPU, smaller (power of two) for small
+// ensembles so that more SMs get a tile, and never more than shared memory allows.
+int pick_C(const rcm_solver* s, int ncol, int nsm) {
+    int C = 64;
+    while (C > 1 && (ncol + C - 1) / C < nsm) C >>= 1;
+    while (C > 1 && rcm_step_smem_bytes(C, s->nactive) > 227 * 1024) C >>= 1;
+    return C;
+}
+
+int launch(rcm_solver* s, int mode, int nsteps, bool want_diag) {
+    int st = refresh_const(s);
+    if (st != RCM_OK) return st;
+    if (!s->has_table) return fail(s, RCM_ERR_STATE, "no lookup table loaded");
+    if (s->ncol <= 0) return fail(s, RCM_ERR_STATE, "no columns loaded");
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, s->device);
+    StepArgs a{};
+    a.ncol = s->ncol;
+    a.C = pick_C(s, s->ncol, nsm);
+    a.ntiles = (s->ncol + a.C - 1) / a.C;
+    a.nsteps = nsteps;
+    a.step_index = s->step_index;
+    a.xsec = s->d_xsec;
+    a.planck_c = s->d_planck_c;
+    a.planck_k = s->d_planck_k;
+    a.Tlayer = s->d_T;
+    a.Tsurf = s->d_Ts;
+    a.vmr = s->d_vmr;
+    a.rel_hum = s->d_rh;
+    a.Tprev = s->d_Tprev;
+    a.time_h = s->d_time;
+    a.E_down = s->d_Ed;
+    a.E_up = s->d_Eu;
+    a.dE = s->d_dE;
+    a.dt = s->d_dt;
+    a.diag = want_diag ? s->d_diag : nullptr;
+    a.tau_io = s->d_tau;
+    a.lowpos_t = s->d_lowpos;
+    a.exp_tab = s->d_exp_tab;
+    a.h2o_slot = s->h2o_slot;
+    const int grid = a.ntiles < nsm ? a.ntiles : nsm;
+    std::pair<cudaEvent_t, cudaEvent_t> ev;
+    if (!s->ev_free.empty()) {
+        ev = s->ev_free.back();
+        s->ev_free.pop_back();
+    } else {
+        CU(cudaEventCreate(&ev.first));
+        CU(cudaEventCreate(&ev.second));
+    }
+    CU(cudaEventRecord(ev.first, s->stream));
+    CU(rcm_launch_step(mode, a, s->nactive, grid, s->stream));
+    CU(cudaEventRecord(ev.second, s->stream));
+    if (mode == MODE_STEP) s->ev_used.push_back(ev); else s->ev_free.push_back(ev);
+    s->launches += 1;
+    if (s->ev_used.size() >= 1024) {  // long runs: fold the finished timings so the pool stays small
+        st = rcm_kernel_time_ms(s, 0, nullptr, nullptr);
+        if (st != RCM_OK) return st;
+    }
+    return RCM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rcm_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int rcm_create(int device, const rcm_params* p, rcm_solver** out) {
+    if (!out) return RCM_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return RCM_ERR_NO_DEVICE;
+    if (device < 0 || device >= n) return RCM_ERR_ARG;
+    rcm_solver* s = new (std::nothrow) rcm_solver();
+    if (!s) return RCM_ERR_NOMEM;
+    s->device = device;
+    if (p) s->p = *p; else rcm_default_params(&s->p);
+    if (s->p.nangle < 1 || s->p.nangle > MAX_ANGLE || s->p.cloud_layer >= RCM_NLAYER) {
+        delete s;
+        return RCM_ERR_ARG;
+    }
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete s;
+        return RCM_ERR_CUDA;
+    }
+    s->stream = s->own_stream;
+    double tab[EXP_TAB];
+    for (int j = 0; j < EXP_TAB; ++j) tab[j] = std::exp2((double)j / EXP_TAB);
+    if (dalloc(s->d_exp_tab, EXP_TAB) != cudaSuccess ||
+        cudaMemcpy(s->d_exp_tab, tab, sizeof(tab), cudaMemcpyHostToDevice) != cudaSuccess) {
+        delete s;
+        return RCM_ERR_CUDA;
+    }
+    set_active_species(s);
+    *out = s;
+    return RCM_OK;
+}
+
+int rcm_destroy(rcm_solver* s) {
+    if (!s) return RCM_OK;
+    cudaSetDevice(s->device);
+    cudaStreamSynchronize(s->stream);
+    void* ptrs[] = {s->d_xsec, s->d_planck_c, s->d_planck_k, s->d_exp_tab, s->d_T, s->d_Ts, s->d_vmr, s->d_rh,
+                    s->d_Tprev, s->d_time, s->d_Ed, s->d_Eu, s->d_dE, s->d_dt, s->d_diag, s->d_scalars, s->d_tau,
+                    s->d_lowpos};
+    for (void* q : ptrs)
+        if (q) cudaFree(q);
+    for (auto& e : s->ev_free) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    for (auto& e : s->ev_used) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    if (s->own_stream) cudaStreamDestroy(s->own_stream);
+    delete s;
+    return RCM_OK;
+}
+
+const char* rcm_last_error(const rcm_solver* s) { return s ? s->err.c_str() : "null solver"; }
+
+int rcm_set_params(rcm_solver* s, const rcm_params* p) {
+    if (!s || !p) return RCM_ERR_ARG;
+    if (p->nangle < 1 || p->nangle > MAX_ANGLE || p->cloud_layer >= RCM_NLAYER) return fail(s, RCM_ERR_ARG, "bad params");
+    unsigned old = s->p.species_mask;
+    s->p = *p;
+    if (old != p->species_mask && s->ncol > 0) s->ncol = 0;  // packed VMR layout changed: columns must be reloaded
+    s->const_dirty = true;
+    set_active_species(s);
+    return RCM_OK;
+}
+
+int rcm_set_option(rcm_solver* s, int option, int value) {
+    if (!s) return RCM_ERR_ARG;
+    if (option == 0) {
+        s->opt_angle_cubes = value ? 1 : 0;
+        s->const_dirty = true;
+        return RCM_OK;
+    }
+    return fail(s, RCM_ERR_ARG, "unknown option");
+}
+
+int rcm_set_stream(rcm_solver* s, void* cuda_stream) {
+    if (!s) return RCM_ERR_ARG;
+    s->stream = cuda_stream ? (cudaStream_t)cuda_stream : s->own_stream;
+    return RCM_OK;
+}
+
+int rcm_synchronize(rcm_solver* s) {
+    if (!s) return RCM_ERR_ARG;
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->stream));
+    return RCM_OK;
+}
+
+int rcm_set_repwvl_table(rcm_solver* s, const double* xsec, const double* wvl, const double* weight,
+                         const double* p_grid, const double* t_ref, const double* t_pert, int n_tpert, int n_species,
+                         int n_wvl, int n_p) {
+    if (!s || !xsec || !wvl || !weight || !p_grid || !t_ref || !t_pert) return RCM_ERR_ARG;
+    if (n_tpert < 2 || n_tpert > MAX_TPERT || n_species != RCM_NSPECIES || n_wvl < 1 || n_p < 2)
+        return fail(s, RCM_ERR_ARG, "unsupported table dimensions");
+    CU(cudaSetDevice(s->device));
+    const size_t n = (size_t)n_tpert * n_species * n_wvl * n_p;
+    double* d_src = nullptr;
+    CU(dalloc(d_src, n));
+    cudaError_t e = cudaMemcpyAsync(d_src, xsec, n * sizeof(double), cudaMemcpyHostToDevice, s->stream);
+    if (e == cudaSuccess) e = dalloc(s->d_xsec, n);
+    if (e == cudaSuccess) e = rcm_launch_relayout(d_src, s->d_xsec, n_tpert, n_species, n_wvl, n_p, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    cudaFree(d_src);
+    if (e != cudaSuccess) return cuda_fail(s, e, "table upload");
+    s->launches += 1;
+    // Planck factors that depend on the wavelength alone (main.cpp:188-191):
+    //   B = w*2*h*c^2 / (lambda^5 * (exp(h*c/(lambda*kB*T)) - 1)) / 1e9
+    const double h = 6.62607e-34, c = 299792458, kB = 1.380649e-23;  // main.cpp:70-72
+    std::vector<double> pc(n_wvl), pk(n_wvl);
+    for (int i = 0; i < n_wvl; ++i) {
+        const double lam = wvl[i] * 1e-9;
+        pc[i] = h * c / (lam * kB);
+        pk[i] = weight[i] * 2 * h * std::pow(c, 2) / std::pow(lam, 5) / 1e9;
+    }
+    CU(dalloc(s->d_planck_c, (size_t)n_wvl));
+    CU(dalloc(s->d_planck_k, (size_t)n_wvl));
+    CU(cudaMemcpy(s->d_planck_c, pc.data(), n_wvl * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(s->d_planck_k, pk.data(), n_wvl * sizeof(double), cudaMemcpyHostToDevice));
+    s->p_grid.assign(p_grid, p_grid + n_p);
+    s->t_ref.assign(t_ref, t_ref + n_p);
+    s->t_pert.assign(t_pert, t_pert + n_tpert);
+    s->wvl.assign(wvl, wvl + n_wvl);
+    s->weight.assign(weight, weight + n_wvl);
+    s->dc.nwvl = n_wvl;
+    s->dc.n_tpert = n_tpert;
+    s->dc.n_species = n_species;
+    s->dc.n_p = n_p;
+    for (int m = 0; m < n_tpert; ++m) s->dc.t_pert[m] = t_pert[m];
+    s->has_table = true;
+    s->const_dirty = true;
+    s->tau_valid = false;
+    s->tau_cap = 0;
+    return RCM_OK;
+}
+
+int rcm_set_repwvl_table_from(rcm_solver* s, const rcm_table* t) {
+    if (!s || !t) return RCM_ERR_ARG;
+    return rcm_set_repwvl_table(s, t->xsec.data(), t->wvl.data(), t->weight.data(), t->p_grid.data(), t->t_ref.data(),
+                                t->t_pert.data(), t->n_tpert, t->n_species, t->n_wvl, t->n_p);
+}
+
+int rcm_set_lbl_tables(rcm_solver* s, const double*, const double*, int, const double*, double) {
+    return fail(s, RCM_ERR_STATE, "line-by-line tables: not available in this build");
+}
+
+int rcm_set_columns(rcm_solver* s, int ncol, const double* plevel_hPa, const double* Tlayer, const double* Tsurf,
+                    const double* vmr9, const double* rel_hum) {
+    if (!s || ncol <= 0 || !plevel_hPa || !Tlayer || !Tsurf || !vmr9 || !rel_hum) return RCM_ERR_ARG;
+    CU(cudaSetDevice(s->device));
+    int st = ensure_columns(s, ncol);
+    if (st != RCM_OK) return st;
+    s->ncol = ncol;
+    std::memcpy(s->plevel, plevel_hPa, sizeof(s->plevel));
+    s->has_plevel = true;
+    s->const_dirty = true;
+    set_active_species(s);
+    const size_t n = (size_t)ncol;
+    // pack the active species rows: [ncol][nactive][20]
+    s->stage.resize(n * s->nactive * NLAY);
+    for (size_t c = 0; c < n; ++c)
+        for (int k = 0; k < s->nactive; ++k)
+            std::memcpy(&s->stage[(c * s->nactive + k) * NLAY], vmr9 + (c * RCM_NSPECIES + s->species[k]) * NLAY,
+                        NLAY * sizeof(double));
+    CU(cudaMemcpyAsync(s->d_vmr, s->stage.data(), s->stage.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->d_T, Tlayer, n * NLAY * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->d_Tprev, Tlayer, n * NLAY * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->d_Ts, Tsurf, n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->d_rh, rel_hum, n * NLAY * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemsetAsync(s->d_time, 0, n * sizeof(float), s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    s->step_index = 0;
+    s->tau_valid = false;
+    return RCM_OK;
+}
+
+int rcm_update_columns(rcm_solver* s, const double* Tlayer, const double* Tsurf, const double* vmr_active) {
+    if (!s) return RCM_ERR_ARG;
+    if (s->ncol <= 0) return fail(s, RCM_ERR_STATE, "rcm_set_columns first");
+    CU(cudaSetDevice(s->device));
+    const size_t n = (size_t)s->ncol;
+    if (Tlayer) CU(cudaMemcpyAsync(s->d_T, Tlayer, n * NLAY * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    if (Tsurf) CU(cudaMemcpyAsync(s->d_Ts, Tsurf, n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    if (vmr_active)
+        CU(cudaMemcpyAsync(s->d_vmr, vmr_active, n * s->nactive * NLAY * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    s->tau_valid = false;
+    return RCM_OK;
+}
+
+int rcm_set_step_index(rcm_solver* s, long step_index) {
+    if (!s || step_index < 0) return RCM_ERR_ARG;
+    s->step_index = step_index;
+    return RCM_OK;
+}
+
+int rcm_build_tau(rcm_solver* s, double* tau_out, int* lowpos_p, int* lowpos_t) {
+    if (!s) return RCM_ERR_ARG;
+    if (!s->has_table || s->ncol <= 0) return fail(s, RCM_ERR_STATE, "table and columns must be loaded");
+    CU(cudaSetDevice(s->device));
+    int st = ensure_tau(s);
+    if (st != RCM_OK) return st;
+    st = launch(s, MODE_TAU, 1, false);
+    if (st != RCM_OK) return st;
+    const size_t n = (size_t)s->ncol;
+    if (tau_out)
+        CU(cudaMemcpyAsync(tau_out, s->d_tau, n * s->dc.nwvl * NLAY * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    std::vector<int> lt;
+    if (lowpos_t) CU(cudaMemcpyAsync(lowpos_t, s->d_lowpos, n * NLAY * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    if (lowpos_p)
+        for (size_t c = 0; c < n; ++c)
+            for (int k = 0; k < NLAY; ++k) lowpos_p[c * NLAY + k] = s->dc.ip[NLAY - 1 - k];
+    s->tau_valid = true;
+    return RCM_OK;
+}
+
+int rcm_radiative_transfer(rcm_solver* s, const double* tau, double* E_down, double* E_up, double* dE) {
+    if (!s) return RCM_ERR_ARG;
+    if (!s->has_table || s->ncol <= 0) return fail(s, RCM_ERR_STATE, "table and columns must be loaded");
+    CU(cudaSetDevice(s->device));
+    int st = ensure_tau(s);
+    if (st != RCM_OK) return st;
+    const size_t n = (size_t)s->ncol;
+    if (tau) {
+        CU(cudaMemcpyAsync(s->d_tau, tau, n * s->dc.nwvl * NLAY * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    } else if (!s->tau_valid) {
+        return fail(s, RCM_ERR_STATE, "no tau: pass one or call rcm_build_tau first");
+    }
+    st = launch(s, MODE_RT, 1, false);
+    if (st != RCM_OK) return st;
+    if (E_down) CU(cudaMemcpyAsync(E_down, s->d_Ed, n * NLEV * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    if (E_up) CU(cudaMemcpyAsync(E_up, s->d_Eu, n * NLEV * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    if (dE) CU(cudaMemcpyAsync(dE, s->d_dE, n * NLAY * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return RCM_OK;
+}
+
+int rcm_advance_async(rcm_solver* s, int nsteps, double** d_scalars) {
+    if (!s || nsteps <= 0) return RCM_ERR_ARG;
+    if (!s->has_table || s->ncol <= 0) return fail(s, RCM_ERR_STATE, "table and columns must be loaded");
+    CU(cudaSetDevice(s->device));
+    int st = ensure_diag(s, nsteps);
+    if (st != RCM_OK) return st;
+    st = launch(s, MODE_STEP, nsteps, true);
+    if (st != RCM_OK) return st;
+    CU(rcm_launch_reduce_diag(s->d_diag, nsteps, s->ncol, s->p.dT_converged, s->d_scalars, s->stream));
+    s->launches += 1;
+    s->step_index += nsteps;
+    s->tau_valid = false;
+    if (d_scalars) *d_scalars = s->d_scalars;
+    return RCM_OK;
+}
+
+int rcm_advance(rcm_solver* s, int nsteps, rcm_step_scalars* scalars_out) {
+    int st = rcm_advance_async(s, nsteps, nullptr);
+    if (st != RCM_OK) return st;
+    if (scalars_out) {
+        CU(cudaMemcpyAsync(scalars_out, s->d_scalars, (size_t)nsteps * sizeof(rcm_step_scalars), cudaMemcpyDeviceToHost,
+                           s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+    }
+    return RCM_OK;
+}
+
+int rcm_get_state(rcm_solver* s, double* Tlayer, double* Tsurf, double* h2o, float* time_h, double* E_down,
+                  double* E_up, double* dE, double* dt) {
+    if (!s) return RCM_ERR_ARG;
+    if (s->ncol <= 0) return fail(s, RCM_ERR_STATE, "no columns loaded");
+    CU(cudaSetDevice(s->device));
+    const size_t n = (size_t)s->ncol;
+    if (Tlayer) CU(cudaMemcpyAsync(Tlayer, s->d_T, n * NLAY * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    if (Tsurf) CU(cudaMemcpyAsync(Tsurf, s->d_Ts, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    if (time_h) CU(cudaMemcpyAsync(time_h, s->d_time, n * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    if (E_down) CU(cudaMemcpyAsync(E_down, s->d_Ed, n * NLEV * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    if (E_up) CU(cudaMemcpyAsync(E_up, s->d_Eu, n * NLEV * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    if (dE) CU(cudaMemcpyAsync(dE, s->d_dE, n * NLAY * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    if (dt) CU(cudaMemcpyAsync(dt, s->d_dt, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    if (h2o) {
+        if (s->h2o_slot < 0) return fail(s, RCM_ERR_STATE, "H2O is not an active species");
+        CU(cudaMemcpy2DAsync(h2o, NLAY * sizeof(double), s->d_vmr + (size_t)s->h2o_slot * NLAY,
+                             (size_t)s->nactive * NLAY * sizeof(double), NLAY * sizeof(double), n, cudaMemcpyDeviceToHost,
+                             s->stream));
+    }
+    CU(cudaStreamSynchronize(s->stream));
+    return RCM_OK;
+}
+
+int rcm_step_host(rcm_solver* s, const double* Tlayer_in, const double* Tsurf_in, const double* vmr_active_in,
+                  double* E_down, double* E_up, double* dE, double* Tlayer_out, double* Tsurf_out) {
+    int st = rcm_update_columns(s, Tlayer_in, Tsurf_in, vmr_active_in);
+    if (st != RCM_OK) return st;
+    st = rcm_advance_async(s, 1, nullptr);
+    if (st != RCM_OK) return st;
+    return rcm_get_state(s, Tlayer_out, Tsurf_out, nullptr, nullptr, E_down, E_up, dE, nullptr);
+}
+
+int rcm_cplkavg_device(rcm_solver* s, int n, const double* lo_nm, const double* hi_nm, const double* t, double* out) {
+    if (!s || n <= 0 || !lo_nm || !hi_nm || !t || !out) return RCM_ERR_ARG;
+    CU(cudaSetDevice(s->device));
+    double* d = nullptr;
+    CU(dalloc(d, (size_t)4 * n));
+    cudaError_t e = cudaMemcpyAsync(d, lo_nm, n * sizeof(double), cudaMemcpyHostToDevice, s->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + n, hi_nm, n * sizeof(double), cudaMemcpyHostToDevice, s->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + 2 * (size_t)n, t, n * sizeof(double), cudaMemcpyHostToDevice, s->stream);
+    if (e == cudaSuccess) e = rcm_launch_cplkavg(n, d, d + n, d + 2 * (size_t)n, d + 3 * (size_t)n, s->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d + 3 * (size_t)n, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return cuda_fail(s, e, "cplkavg");
+    s->launches += 1;
+    return RCM_OK;
+}
+
+long rcm_launch_count(const rcm_solver* s) { return s ? s->launches : 0; }
+
+int rcm_fp64_microbench(rcm_solver* s, int which, double* gops) {
+    if (!s || !gops || which < 0 || which > 3) return RCM_ERR_ARG;
+    CU(cudaSetDevice(s->device));
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, s->device);
+    const int grid = nsm * 8;
+    const long iters = (which == 0) ? 40000 : 4000;
+    double* d = nullptr;
+    CU(dalloc(d, (size_t)grid * 256));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaError_t e = rcm_launch_microbench(which, d, s->d_exp_tab, iters / 10, grid, s->stream);  // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 3 && e == cudaSuccess; ++rep) {
+        cudaEventRecord(e0, s->stream);
+        e = rcm_launch_microbench(which, d, s->d_exp_tab, iters, grid, s->stream);
+        cudaEventRecord(e1, s->stream);
+        if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    if (e != cudaSuccess) return cuda_fail(s, e, "microbench");
+    s->launches += 4;
+    *gops = (double)grid * 256.0 * 8.0 * (double)iters / (best * 1e-3) / 1e9;
+    return RCM_OK;
+}
+
+int rcm_kernel_time_ms(rcm_solver* s, int reset, double* avg_ms, long* n_launches) {
+    if (!s) return RCM_ERR_ARG;
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->stream));
+    for (auto& ev : s->ev_used) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) {
+            s->kt_ms += ms;
+            s->kt_n += 1;
+        }
+        s->ev_free.push_back(ev);
+    }
+    s->ev_used.clear();
+    if (avg_ms) *avg_ms = s->kt_n ? s->kt_ms / s->kt_n : 0.0;
+    if (n_launches) *n_launches = s->kt_n;
+    if (reset) {
+        s->kt_ms = 0.0;
+        s->kt_n = 0;
+    }
+    return RCM_OK;
+}
+
+}  // extern "C"

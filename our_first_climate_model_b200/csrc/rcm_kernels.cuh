@@ -1,0 +1,81 @@
+// Device side of the B200-native column solver: declarations shared with rcm_capi.cu.
+#ifndef RCM_KERNELS_CUH
+#define RCM_KERNELS_CUH
+
+#include <cuda_runtime.h>
+
+#include "rcm_internal.h"
+
+constexpr int NLAY = RCM_NLAYER;
+constexpr int NLEV = RCM_NLEVEL;
+constexpr int MAX_ANGLE = 64;
+constexpr int MAX_TPERT = 16;
+constexpr int RCM_THREADS = 256;   // threads per CTA of the step kernel (2 warps per SM sub-partition)
+constexpr int EXP_TAB = 64;        // entries of the 2^(j/64) table used by the solver's exp
+
+// Everything that is uniform over the ensemble.  Lives in __constant__ memory.
+struct DevConst {
+    int nwvl, nangle, nactive, n_tpert, n_species, n_p;
+    int species[RCM_NSPECIES];  // active species, ascending
+    int cloud_layer;
+    double cloud_tau, dp, max_dT, dt_cap, solar_irr, dT_converged;
+    // per layer (top-down index l), from the shared pressure grid - host computed with the
+    // reference's expressions (repwvl_thermal.cpp:202, :214, :226, :240)
+    int ip[NLAY];
+    double delP[NLAY], numDens[NLAY], tref_ip[NLAY], player[NLAY], conv[NLAY];
+    double t_pert[MAX_TPERT];
+    // angle schedule: slot a holds quadrature node n_a (1/mu = 2*nangle/n_a ... see capi) either
+    // evaluated with exp (head) or derived by cubing the transmissions of the previous slot
+    double neg_inv_mu[MAX_ANGLE];  // -1/mu of the slot
+    double cmu[MAX_ANGLE];         // 2*pi*mu*dmu of the slot
+    int cube[MAX_ANGLE];           // 1: t <- t^3 from the previous slot, 0: exp
+    double csum;                   // sum of cmu
+    // LBL band edges etc. live in global memory
+};
+
+// Per-launch arguments (pointers into the solver's device allocations).
+struct StepArgs {
+    int ncol;            // columns in this launch
+    int C;               // columns per tile (RCM_THREADS % C == 0)
+    int ntiles;
+    int nsteps;          // time steps fused in this launch
+    long step_index;     // global index of the first step (0 => initial-profile tau, main.cpp:500-504)
+    // table, re-laid out as xsec[ip][it][species][wvl]
+    const double* __restrict__ xsec;
+    const double* __restrict__ planck_c;  // [nwvl] h*c/(lambda*kB)   [K]
+    const double* __restrict__ planck_k;  // [nwvl] weight*2*h*c^2/lambda^5/1e9
+    // column state
+    double* Tlayer;        // [ncol][20]
+    double* Tsurf;         // [ncol]
+    double* vmr;           // [ncol][nactive][20]
+    const double* rel_hum; // [ncol][20]
+    double* Tprev;         // [ncol][20] sorted profile of the previous step
+    float* time_h;         // [ncol]
+    // outputs of the last step
+    double* E_down;        // [ncol][21]
+    double* E_up;          // [ncol][21]
+    double* dE;            // [ncol][20]
+    double* dt;            // [ncol]
+    double* diag;          // [nsteps][ncol][4]  toa_net, dT_stat, max|dE|, spare   (NULL = skip)
+    // component paths
+    double* tau_io;        // [ncol][nwvl][20]  (written by MODE_TAU, read by MODE_RT)
+    int* lowpos_t;         // [ncol][20] bottom-up (MODE_TAU)
+    const double* exp_tab; // [64] 2^(j/64)
+    int h2o_slot;          // position of H2O in the active list, -1 if absent
+};
+
+enum { MODE_STEP = 0, MODE_TAU = 1, MODE_RT = 2 };
+
+size_t rcm_step_smem_bytes(int C, int nactive);
+cudaError_t rcm_upload_const(const DevConst& c);
+cudaError_t rcm_launch_step(int mode, const StepArgs& a, int nactive, int grid, cudaStream_t st);
+cudaError_t rcm_launch_reduce_diag(const double* diag, int nsteps, int ncol, double dT_converged, double* scalars,
+                                   cudaStream_t st);
+cudaError_t rcm_launch_relayout(const double* xsec_file, double* xsec_dev, int nt, int ns, int nw, int np,
+                                cudaStream_t st);
+cudaError_t rcm_launch_microbench(int which, double* out, const double* tab, long iters, int grid,
+                                  cudaStream_t st);
+cudaError_t rcm_launch_cplkavg(int n, const double* lo, const double* hi, const double* t, double* out,
+                               cudaStream_t st);
+
+#endif
