@@ -21,10 +21,14 @@ struct rcm_solver {
     DevConst dc{};
     bool const_dirty = true;
     int opt_angle_cubes = 1;
+    int opt_config = 1;        // 0: 512 threads x 64 columns, 1: 256 threads x 32 columns (2 CTAs/SM), 2: 384x64, 3: 192x32
+    int opt_stagger = 0;       // de-phasing delay in cycles (0 = off)
     // table
     bool has_table = false;
     std::vector<double> p_grid, t_ref, t_pert, wvl, weight;
-    double *d_xsec = nullptr, *d_planck_c = nullptr, *d_planck_k = nullptr, *d_exp_tab = nullptr;
+    double *d_xsec_file = nullptr, *d_coef = nullptr, *d_planck_c = nullptr, *d_planck_k = nullptr, *d_exp_tab = nullptr;
+    int* d_species = nullptr;
+    bool coef_dirty = true;
     // columns
     int ncol = 0, cap = 0, nactive = 0, h2o_slot = -1;
     int species[RCM_NSPECIES]{};
@@ -116,7 +120,7 @@ void build_angles(rcm_solver* s) {
     double sum = 0.0;
     for (int a = 0; a < na; ++a) {
         const double mu = dmu / 2.0 + dmu * (double)order[a];
-        d.neg_inv_mu[a] = -1.0 / mu;
+        d.neg_inv_mu_l2e[a] = (-1.0 / mu) * 92.33248261689366;  // times 64/ln2, see exp_scaled
         d.cmu[a] = 2 * M_PI * mu * dmu;
         d.cube[a] = cube[a];
         sum += d.cmu[a];
@@ -131,6 +135,7 @@ int refresh_const(rcm_solver* s) {
     d.nactive = s->nactive;
     for (int k = 0; k < RCM_NSPECIES; ++k) d.species[k] = (k < s->nactive) ? s->species[k] : 0;
     d.cloud_layer = s->p.cloud_layer;
+    d.cloud_row = s->p.cloud_layer < 0 ? -1 : (s->p.cloud_layer < HALF ? s->p.cloud_layer : 29 - s->p.cloud_layer);
     d.cloud_tau = s->p.cloud_tau;
     d.dp = s->p.dp;
     d.max_dT = s->p.max_dT;
@@ -146,12 +151,14 @@ int refresh_const(rcm_solver* s) {
         for (int k = 0; k < RCM_NLEVEL; ++k) P[k] = s->plevel[RCM_NLEVEL - 1 - k] * 100.0;
         for (int k = 0; k < RCM_NLAYER; ++k) {
             const int l = RCM_NLAYER - 1 - k;
+            const int r = l < HALF ? l : 29 - l;  // pair-order row (see rcm_kernels.cu)
             const double midP = (P[k + 1] + P[k]) / 2;
             const long ip = rcm_lowerpos_impl(s->p_grid.data(), (int)s->p_grid.size(), midP);
             d.ip[l] = (int)ip;
-            d.delP[l] = (midP - s->p_grid[ip]) / (s->p_grid[ip + 1] - s->p_grid[ip]);
-            d.numDens[l] = (P[k] - P[k + 1]) * avog / molMassAir / earthAccel;
-            d.tref_ip[l] = s->t_ref[ip];
+            d.ipcell[r] = (int)ip * (d.n_tpert - 1);
+            d.delP[r] = (midP - s->p_grid[ip]) / (s->p_grid[ip + 1] - s->p_grid[ip]);
+            d.numDens[r] = (P[k] - P[k + 1]) * avog / molMassAir / earthAccel;
+            d.tref_ip[r] = s->t_ref[ip];
         }
     }
     if (s->has_plevel) {
@@ -162,6 +169,18 @@ int refresh_const(rcm_solver* s) {
     }
     cudaError_t e = rcm_upload_const(d);
     if (e != cudaSuccess) return cuda_fail(s, e, "upload constants");
+    if (s->has_table && s->coef_dirty) {
+        // bilinear coefficients of the active species: coef[cell][wvl][k][4]
+        const size_t n = (size_t)(d.n_p - 1) * (d.n_tpert - 1) * d.nwvl * s->nactive * 4;
+        CU(dalloc(s->d_coef, n));
+        CU(dalloc(s->d_species, (size_t)RCM_NSPECIES));
+        CU(cudaMemcpyAsync(s->d_species, s->species, sizeof(s->species), cudaMemcpyHostToDevice, s->stream));
+        CU(rcm_launch_coef(s->d_xsec_file, s->d_coef, d.n_tpert, d.n_species, d.nwvl, d.n_p, s->nactive, s->d_species,
+                           s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+        s->launches += 1;
+        s->coef_dirty = false;
+    }
     s->const_dirty = false;
     return RCM_OK;
 }
@@ -201,13 +220,11 @@ int ensure_tau(rcm_solver* s) {
     return RCM_OK;
 }
 
-// Columns per tile: 64 when the ensemble fills the GPU, smaller (power of two) for small
-// ensembles so that more SMs get a tile, and never more than shared memory allows.
+// Columns per tile: 64 when that still gives every SM a tile (and shared memory allows), else 16.
 int pick_C(const rcm_solver* s, int ncol, int nsm) {
-    int C = 64;
-    while (C > 1 && (ncol + C - 1) / C < nsm) C >>= 1;
-    while (C > 1 && rcm_step_smem_bytes(C, s->nactive) > 227 * 1024) C >>= 1;
-    return C;
+    if ((ncol + 63) / 64 >= nsm && rcm_step_smem_bytes(64, s->nactive, 512) <= 227 * 1024)
+        return (s->opt_config == 1 || s->opt_config == 3) ? 32 : 64;
+    return 16;
 }
 
 int launch(rcm_solver* s, int mode, int nsteps, bool want_diag) {
@@ -221,9 +238,12 @@ int launch(rcm_solver* s, int mode, int nsteps, bool want_diag) {
     a.ncol = s->ncol;
     a.C = pick_C(s, s->ncol, nsm);
     a.ntiles = (s->ncol + a.C - 1) / a.C;
+    a.nthreads = (a.C == 32) ? (s->opt_config == 3 ? 192 : 256) : ((a.C == 64 && s->opt_config == 2) ? 384 : 512);
+    a.stagger_mode = (a.C == 32) ? 1 : 0;
+    a.stagger_cycles = s->opt_stagger;
     a.nsteps = nsteps;
     a.step_index = s->step_index;
-    a.xsec = s->d_xsec;
+    a.coef = s->d_coef;
     a.planck_c = s->d_planck_c;
     a.planck_k = s->d_planck_k;
     a.Tlayer = s->d_T;
@@ -241,7 +261,8 @@ int launch(rcm_solver* s, int mode, int nsteps, bool want_diag) {
     a.lowpos_t = s->d_lowpos;
     a.exp_tab = s->d_exp_tab;
     a.h2o_slot = s->h2o_slot;
-    const int grid = a.ntiles < nsm ? a.ntiles : nsm;
+    const int ctas = nsm * (a.nthreads <= 256 ? 2 : 1);
+    const int grid = a.ntiles < ctas ? a.ntiles : ctas;
     std::pair<cudaEvent_t, cudaEvent_t> ev;
     if (!s->ev_free.empty()) {
         ev = s->ev_free.back();
@@ -307,7 +328,7 @@ int rcm_destroy(rcm_solver* s) {
     if (!s) return RCM_OK;
     cudaSetDevice(s->device);
     cudaStreamSynchronize(s->stream);
-    void* ptrs[] = {s->d_xsec, s->d_planck_c, s->d_planck_k, s->d_exp_tab, s->d_T, s->d_Ts, s->d_vmr, s->d_rh,
+    void* ptrs[] = {s->d_xsec_file, s->d_coef, s->d_species, s->d_planck_c, s->d_planck_k, s->d_exp_tab, s->d_T, s->d_Ts, s->d_vmr, s->d_rh,
                     s->d_Tprev, s->d_time, s->d_Ed, s->d_Eu, s->d_dE, s->d_dt, s->d_diag, s->d_scalars, s->d_tau,
                     s->d_lowpos};
     for (void* q : ptrs)
@@ -326,7 +347,10 @@ int rcm_set_params(rcm_solver* s, const rcm_params* p) {
     if (p->nangle < 1 || p->nangle > MAX_ANGLE || p->cloud_layer >= RCM_NLAYER) return fail(s, RCM_ERR_ARG, "bad params");
     unsigned old = s->p.species_mask;
     s->p = *p;
-    if (old != p->species_mask && s->ncol > 0) s->ncol = 0;  // packed VMR layout changed: columns must be reloaded
+    if (old != p->species_mask) {
+        s->coef_dirty = true;
+        s->ncol = 0;  // packed VMR layout changed: columns must be reloaded
+    }
     s->const_dirty = true;
     set_active_species(s);
     return RCM_OK;
@@ -337,6 +361,14 @@ int rcm_set_option(rcm_solver* s, int option, int value) {
     if (option == 0) {
         s->opt_angle_cubes = value ? 1 : 0;
         s->const_dirty = true;
+        return RCM_OK;
+    }
+    if (option == 1) {
+        s->opt_config = value;
+        return RCM_OK;
+    }
+    if (option == 2) {
+        s->opt_stagger = value;
         return RCM_OK;
     }
     return fail(s, RCM_ERR_ARG, "unknown option");
@@ -363,15 +395,9 @@ int rcm_set_repwvl_table(rcm_solver* s, const double* xsec, const double* wvl, c
         return fail(s, RCM_ERR_ARG, "unsupported table dimensions");
     CU(cudaSetDevice(s->device));
     const size_t n = (size_t)n_tpert * n_species * n_wvl * n_p;
-    double* d_src = nullptr;
-    CU(dalloc(d_src, n));
-    cudaError_t e = cudaMemcpyAsync(d_src, xsec, n * sizeof(double), cudaMemcpyHostToDevice, s->stream);
-    if (e == cudaSuccess) e = dalloc(s->d_xsec, n);
-    if (e == cudaSuccess) e = rcm_launch_relayout(d_src, s->d_xsec, n_tpert, n_species, n_wvl, n_p, s->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
-    cudaFree(d_src);
-    if (e != cudaSuccess) return cuda_fail(s, e, "table upload");
-    s->launches += 1;
+    CU(dalloc(s->d_xsec_file, n));
+    CU(cudaMemcpy(s->d_xsec_file, xsec, n * sizeof(double), cudaMemcpyHostToDevice));
+    s->coef_dirty = true;
     // Planck factors that depend on the wavelength alone (main.cpp:188-191):
     //   B = w*2*h*c^2 / (lambda^5 * (exp(h*c/(lambda*kB*T)) - 1)) / 1e9
     const double h = 6.62607e-34, c = 299792458, kB = 1.380649e-23;  // main.cpp:70-72

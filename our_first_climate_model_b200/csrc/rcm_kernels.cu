@@ -29,30 +29,33 @@ cudaError_t rcm_upload_const(const DevConst& c) { return cudaMemcpyToSymbol(cst,
 namespace {
 
 // ------------------------------------------------------------------------------------------
-// exp(x) for the transmission t = exp(-tau/mu).  x = k*ln2/64 + r with k = round(x*64/ln2);
-// exp(x) = 2^(k>>6) * 2^((k&63)/64) * exp(r), |r| <= ln2/128, exp(r) by a degree-5 polynomial
-// (truncation 3.5e-17 relative).  10 FP64-pipe instructions and one conflict-free LDS.64
-// (the 64-entry table is replicated per lane: tab[j*32 + lane]) instead of ~17 for exp().
-// Valid for |x| <= 700; more negative arguments are clamped (exp(-700) ~ 1e-304 ~ 0).
+// exp of (a*b) for the transmissions t = exp(-tau/mu) and the Planck exponent.  With
+// z = a*b*64/ln2 (the caller passes b already scaled by 64/ln2), k = round(z), f = z - k:
+//   exp = 2^(k>>6) * 2^((k&63)/64) * exp(f*ln2/64),  |f| <= 1/2,
+// exp(f*c) - 1 = f*h(f) with a degree-4 Horner h (truncation 3.5e-17 relative).
+// 9 FP64-pipe instructions + 6 integer/LDS instructions (CUDA's exp(): ~16 + 8).  The 64-entry
+// table 2^(j/64) is replicated per lane (tab[j*32 + lane]) so the LDS.64 never bank-conflicts.
+// The power of two is clamped at 2^-1000 (result ~1e-301, i.e. 0 for every use here); valid up
+// to exp(+700).
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ double exp_tab(double x, const double* __restrict__ tab_lane) {
-    const unsigned hi = (unsigned)__double2hiint(x);
-    if (hi > 0xC085E000u) x = -700.0;  // x < -700 (sign bit set, larger magnitude)
-    const double SHIFT = 6755399441055744.0;  // 1.5 * 2^52: the add leaves round(x*64/ln2) in the low word
-    const double t = fma(x, 92.33248261689366, SHIFT);  // 64/ln2
+__device__ __forceinline__ double exp_scaled(double a, double b_l2e64, const double* __restrict__ tab_lane) {
+    const double SHIFT = 6755399441055744.0;  // 1.5 * 2^52: the add leaves round(z) in the low word
+    const double t = fma(a, b_l2e64, SHIFT);
     const int k = __double2loint(t);
     const double kd = t - SHIFT;
-    double r = fma(kd, -0x1.62e42fee00000p-7, x);        // ln2/64, high 32 bits (k * hi is exact)
-    r = fma(kd, -0x1.a39ef35793c76p-39, r);              // ln2/64 - hi
+    const double f = fma(a, b_l2e64, -kd);  // exact product minus an integer: one rounding
     const double T = tab_lane[(k & (EXP_TAB - 1)) << 5];
-    double p = fma(r, 8.3333333333333332e-03, 4.1666666666666664e-02);
-    p = fma(r, p, 1.6666666666666666e-01);
-    p = fma(r, p, 0.5);
-    const double r2 = r * r;
-    const double q = fma(r2, p, r);
-    const double y = fma(T, q, T);
-    return __hiloint2double(__double2hiint(y) + ((k >> 6) << 20), __double2loint(y));
+    double h = fma(f, 0x1.5d87fe78a6731p-40, 0x1.3b2ab6fba4e77p-31);  // c^5/120, c^4/24   (c = ln2/64)
+    h = fma(f, h, 0x1.c6b08d704a0c0p-23);                              // c^3/6
+    h = fma(f, h, 0x1.ebfbdff82c58fp-15);                              // c^2/2
+    h = fma(f, h, 0x1.62e42fefa39efp-7);                               // c
+    const double u = T * f;
+    const double y = fma(u, h, T);
+    const int m = max(k >> 6, -1000);
+    return __hiloint2double(__double2hiint(y) + (m << 20), __double2loint(y));
 }
+
+constexpr double L2E64 = 0x1.71547652b82fep+6;  // 64/ln2
 
 // descending compare-exchange
 __device__ __forceinline__ void cex(double& a, double& b) {
@@ -61,7 +64,7 @@ __device__ __forceinline__ void cex(double& a, double& b) {
     b = lo;
 }
 
-// LowerPos (repwvl_thermal.cpp:19-45) on the nine perturbed temperatures of one pressure node.
+// LowerPos (repwvl_thermal.cpp:19-45) on the perturbed temperatures of one pressure node.
 __device__ __forceinline__ int lowerpos_t(double tref, double x, int n) {
     auto sgn = [](double v) { return (0.0 < v) - (v < 0.0); };
     int prev = sgn((tref + cst.t_pert[0]) - x);
@@ -78,48 +81,52 @@ __device__ __forceinline__ int lowerpos_t(double tref, double x, int n) {
     return res;
 }
 
+// Layer split.  The two lanes of a pair share one (column, wavelength): lane h=0 owns layers 0..9
+// top-down, lane h=1 owns layers 19..10 (bottom-up), both as local index j=0..9.  Per-layer
+// arrays are stored in this order: row(l) = l for l<10, 29-l otherwise (= 10*h + j).
+__device__ __forceinline__ constexpr int prow(int l) { return l < HALF ? l : 29 - l; }
+
+template <int C, int NT>
 struct Smem {
     double* exp_tab;  // [64][32]
-    double* T;        // [20][C] layer temperature used for the source (sorted)
+    double* T;        // [20][C] layer temperature (sorted), rows in pair order
     double* invT;     // [20][C]
     double* delT;     // [20][C]
-    double* dE;       // [20][C]
+    double* dE;       // [20][C]   natural layer order
     double* vmr;      // [nactive][20][C]
-    double* Ep;       // [21][RCM_THREADS] reduction staging
-    double* Ed;       // [21][C]
+    double* Ep;       // [21][NT/2] reduction staging
+    double* Ed;       // [21][C]   natural level order
     double* Eu;       // [21][C]
-    double* Ts;       // [C] surface temperature
+    double* Ts;       // [C]
     double* invTs;    // [C]
     double* dt;       // [C]
     int* it;          // [20][C]
+    __device__ __forceinline__ Smem(unsigned char* base, int nactive) {
+        double* p = reinterpret_cast<double*>(base);
+        exp_tab = p; p += EXP_TAB * 32;
+        T = p;       p += NLAY * C;
+        invT = p;    p += NLAY * C;
+        delT = p;    p += NLAY * C;
+        dE = p;      p += NLAY * C;
+        vmr = p;     p += nactive * NLAY * C;
+        Ep = p;      p += NLEV * (NT / 2);
+        Ed = p;      p += NLEV * C;
+        Eu = p;      p += NLEV * C;
+        Ts = p;      p += C;
+        invTs = p;   p += C;
+        dt = p;      p += C;
+        it = reinterpret_cast<int*>(p);
+    }
 };
-
-__device__ __forceinline__ Smem carve(unsigned char* base, int C, int nactive) {
-    Smem s;
-    double* p = reinterpret_cast<double*>(base);
-    s.exp_tab = p; p += EXP_TAB * 32;
-    s.T = p;       p += NLAY * C;
-    s.invT = p;    p += NLAY * C;
-    s.delT = p;    p += NLAY * C;
-    s.dE = p;      p += NLAY * C;
-    s.vmr = p;     p += nactive * NLAY * C;
-    s.Ep = p;      p += NLEV * RCM_THREADS;
-    s.Ed = p;      p += NLEV * C;
-    s.Eu = p;      p += NLEV * C;
-    s.Ts = p;      p += C;
-    s.invTs = p;   p += C;
-    s.dt = p;      p += C;
-    s.it = reinterpret_cast<int*>(p);
-    return s;
-}
 
 // Table indices and interpolation weights in T for every (layer, column) of the tile, from the
 // temperatures currently in s.T (repwvl_thermal.cpp:229-239).
-__device__ __forceinline__ void prep_tau_indices(const Smem& s, int C, int tid) {
-    for (int i = tid; i < NLAY * C; i += RCM_THREADS) {
-        const int l = i / C;
+template <int C, int NT>
+__device__ __forceinline__ void prep_tau_indices(const Smem<C, NT>& s, int tid) {
+    for (int i = tid; i < NLAY * C; i += NT) {
+        const int r = i / C;  // pair-order row; tref_ip is stored in the same order
         const double midT = s.T[i];
-        const double tref = cst.tref_ip[l];
+        const double tref = cst.tref_ip[r];
         const int it = lowerpos_t(tref, midT, cst.n_tpert);
         const double t0 = tref + cst.t_pert[it], t1 = tref + cst.t_pert[it + 1];
         s.it[i] = it;
@@ -127,20 +134,19 @@ __device__ __forceinline__ void prep_tau_indices(const Smem& s, int C, int tid) 
     }
 }
 
-template <int MODE, int NACT>
-__global__ void __launch_bounds__(RCM_THREADS, 1) rcm_step_kernel(const StepArgs a) {
+template <int MODE, int NACT, int C, int NT>
+__global__ void __launch_bounds__(NT, 512 / NT) rcm_step_kernel(const StepArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int G = NT / (2 * C);  // wavelength groups
     const int tid = threadIdx.x, lane = tid & 31;
-    const int C = a.C, G = RCM_THREADS / C;
+    const int h = tid & 1, q = tid >> 1, c = q % C, g = q / C;
     const int nact = (NACT > 0) ? NACT : cst.nactive;
-    const Smem s = carve(smem_raw, C, nact);
-    const int c = tid % C, g = tid / C;
+    const Smem<C, NT> s(smem_raw, nact);
+    const int sb = h * HALF * C + c;  // this thread's row block in the per-layer arrays
 
-    for (int i = tid; i < EXP_TAB * 32; i += RCM_THREADS) s.exp_tab[i] = a.exp_tab[i >> 5];
+    for (int i = tid; i < EXP_TAB * 32; i += NT) s.exp_tab[i] = a.exp_tab[i >> 5];
     const double* tab_lane = s.exp_tab + lane;
     const int nang = cst.nangle, nwvl = cst.nwvl;
-    const size_t xs_it = (size_t)cst.n_species * nwvl;  // stride of the T-perturbation index
-    const size_t xs_ip = xs_it * cst.n_tpert;           // stride of the pressure index
 
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
         const int col0 = tile * C;
@@ -148,13 +154,14 @@ __global__ void __launch_bounds__(RCM_THREADS, 1) rcm_step_kernel(const StepArgs
         const bool live = c < ncl;
         __syncthreads();
         // ---- load the tile's state: T [20][C], surface T, active VMRs -----------------------
-        for (int i = tid; i < NLAY * C; i += RCM_THREADS) {
+        for (int i = tid; i < NLAY * C; i += NT) {
             const int l = i / C, cc = i % C;
-            s.T[i] = (cc < ncl) ? a.Tlayer[(size_t)(col0 + cc) * NLAY + l] : 250.0;
+            s.T[prow(l) * C + cc] = (cc < ncl) ? a.Tlayer[(size_t)(col0 + cc) * NLAY + l] : 250.0;
         }
-        for (int i = tid; i < nact * NLAY * C; i += RCM_THREADS) {
+        for (int i = tid; i < nact * NLAY * C; i += NT) {
             const int cc = i % C, l = (i / C) % NLAY, sp = i / (C * NLAY);
-            s.vmr[i] = (cc < ncl) ? a.vmr[((size_t)(col0 + cc) * nact + sp) * NLAY + l] : 0.0;
+            s.vmr[(sp * NLAY + prow(l)) * C + cc] =
+                (cc < ncl) ? a.vmr[((size_t)(col0 + cc) * nact + sp) * NLAY + l] : 0.0;
         }
         if (tid < C) s.Ts[tid] = (tid < ncl) ? a.Tsurf[col0 + tid] : 250.0;
         __syncthreads();
@@ -164,13 +171,13 @@ __global__ void __launch_bounds__(RCM_THREADS, 1) rcm_step_kernel(const StepArgs
             // ---------------- K5a: adjustment, feedback, table indices ------------------------
             if (MODE == MODE_STEP) {
                 if (first) {  // tau of the initial profile is built BEFORE the first sort (main.cpp:500-504)
-                    prep_tau_indices(s, C, tid);
+                    prep_tau_indices(s, tid);
                     __syncthreads();
                 }
                 if (tid < C) {  // theta-sort, one thread per column (main.cpp:536-540)
                     double th[NLAY];
 #pragma unroll
-                    for (int l = 0; l < NLAY; ++l) th[l] = s.T[l * C + tid] * cst.conv[l];
+                    for (int l = 0; l < NLAY; ++l) th[l] = s.T[prow(l) * C + tid] * cst.conv[l];
 #pragma unroll
                     for (int pass = 0; pass < NLAY; ++pass) {
 #pragma unroll
@@ -180,7 +187,7 @@ __global__ void __launch_bounds__(RCM_THREADS, 1) rcm_step_kernel(const StepArgs
 #pragma unroll
                     for (int l = 0; l < NLAY; ++l) {
                         const double Tn = th[l] / cst.conv[l];
-                        s.T[l * C + tid] = Tn;
+                        s.T[prow(l) * C + tid] = Tn;
                         if (tid < ncl) {
                             const size_t gi = (size_t)(col0 + tid) * NLAY + l;
                             dmax = fmax(dmax, fabs(Tn - a.Tprev[gi]));
@@ -193,74 +200,90 @@ __global__ void __launch_bounds__(RCM_THREADS, 1) rcm_step_kernel(const StepArgs
                 if (!first) {
                     // water_vapor_feedback (main.cpp:281-289) then indices from the sorted profile
                     if (a.h2o_slot >= 0) {
-                        for (int i = tid; i < NLAY * C; i += RCM_THREADS) {
+                        for (int i = tid; i < NLAY * C; i += NT) {
                             const int l = i / C, cc = i % C;
                             if (cc < ncl) {
-                                const double Tc = s.T[i] - 273.15;
+                                const int r = prow(l) * C + cc;
+                                const double Tc = s.T[r] - 273.15;
                                 const double e_sat = 6.1094 * exp(17.625 * Tc / (Tc + 243.04));
                                 const double rh = a.rel_hum[(size_t)(col0 + cc) * NLAY + l];
-                                s.vmr[a.h2o_slot * NLAY * C + i] = rh * e_sat / cst.player[l];
+                                s.vmr[a.h2o_slot * NLAY * C + r] = rh * e_sat / cst.player[l];
                             }
                         }
                     }
-                    prep_tau_indices(s, C, tid);
+                    prep_tau_indices(s, tid);
                 }
             } else if (MODE == MODE_TAU) {
-                prep_tau_indices(s, C, tid);
+                prep_tau_indices(s, tid);
             }
-            for (int i = tid; i < NLAY * C; i += RCM_THREADS) s.invT[i] = 1.0 / s.T[i];
+            for (int i = tid; i < NLAY * C; i += NT) s.invT[i] = 1.0 / s.T[i];
             if (tid < C) s.invTs[tid] = 1.0 / s.Ts[tid];
             __syncthreads();
             if (MODE == MODE_TAU && a.lowpos_t) {
-                for (int i = tid; i < NLAY * C; i += RCM_THREADS) {
+                for (int i = tid; i < NLAY * C; i += NT) {
                     const int l = i / C, cc = i % C;
-                    if (cc < ncl) a.lowpos_t[(size_t)(col0 + cc) * NLAY + (NLAY - 1 - l)] = s.it[i];
+                    if (cc < ncl) a.lowpos_t[(size_t)(col0 + cc) * NLAY + (NLAY - 1 - l)] = s.it[prow(l) * C + cc];
                 }
             }
 
-            // ---------------- K1-K4: per (column, wavelength) work in registers ----------------
-            double Ed[NLAY], Eu[NLAY], Eu20 = 0.0;  // E_down[1..20], E_up[0..19], E_up[20]
+            // ---------------- K1-K4: per (column, wavelength, half) work in registers -----------
+            // E1[j]: flux of the first sweep  (h=0: E_down[j+1],   h=1: E_up[19-j])
+            // E2[j]: flux of the second sweep (h=0: E_up[j],       h=1: E_down[20-j])
+            double E1[HALF], E2[HALF], Eu20 = 0.0;
 #pragma unroll
-            for (int l = 0; l < NLAY; ++l) Ed[l] = Eu[l] = 0.0;
+            for (int j = 0; j < HALF; ++j) E1[j] = E2[j] = 0.0;
 
+            if (MODE == MODE_STEP && a.stagger_cycles > 0) {
+                // De-phase the warps: every second wavelength group (or CTA) starts half an item later, so its
+                // latency-bound tau/Planck phase overlaps the issue-bound angle loop of the others.
+                const bool late = (a.stagger_mode == 0) ? (g & 1) : (blockIdx.x & 1);
+                if (late && (a.stagger_mode == 0 || (step == 0 && tile == (int)blockIdx.x))) {
+                    const long long t0 = clock64();
+                    while (clock64() - t0 < a.stagger_cycles) {
+                    }
+                }
+            }
             for (int w = g; w < nwvl; w += G) {
-                double tau[NLAY];
-                // K1: bilinear (p,T) interpolation of the cross sections, reference operation order,
-                // no FMA contraction -> tau is bit-identical to read_tau's for identical inputs.
+                double tau[HALF];
+                // K1: bilinear (p,T) interpolation of the cross sections in the reference's operation
+                // order, no FMA contraction -> tau is bit-identical to read_tau's for identical inputs.
+                // The four bilinear coefficients c0, cT, cP, cPT (repwvl_thermal.cpp:235-238) depend on
+                // the table alone and are precomputed per cell (rcm_coef_kernel).
                 if (MODE == MODE_RT) {
 #pragma unroll
-                    for (int l = 0; l < NLAY; ++l)
-                        tau[l] = live ? a.tau_io[((size_t)(col0 + c) * nwvl + w) * NLAY + l] : 0.0;
+                    for (int j = 0; j < HALF; ++j) {
+                        const int l = h ? (NLAY - 1 - j) : j;
+                        tau[j] = live ? a.tau_io[((size_t)(col0 + c) * nwvl + w) * NLAY + l] : 0.0;
+                    }
                 } else {
 #pragma unroll
-                    for (int l = 0; l < NLAY; ++l) {
-                        const int it = s.it[l * C + c];
-                        const double dT = s.delT[l * C + c], dP = cst.delP[l];
-                        const double* x0 = a.xsec + (size_t)cst.ip[l] * xs_ip + (size_t)it * xs_it + w;
+                    for (int j = 0; j < HALF; ++j) {
+                        const int r = h * HALF + j;
+                        const int it = s.it[sb + j * C];
+                        const double dT = s.delT[sb + j * C], dP = cst.delP[r];
+                        const double2* cf = reinterpret_cast<const double2*>(a.coef) +
+                                            ((size_t)(cst.ipcell[r] + it) * nwvl + w) * (2 * nact);
                         double acc = 0.0;
 #pragma unroll
                         for (int k = 0; k < (NACT > 0 ? NACT : RCM_NSPECIES); ++k) {
                             if (NACT == 0 && k >= nact) break;
-                            const double* x = x0 + (size_t)cst.species[k] * nwvl;
-                            const double c0 = __ldg(x);
-                            const double cT = __dsub_rn(__ldg(x + xs_it), c0);
-                            const double cP = __dsub_rn(__ldg(x + xs_ip), c0);
-                            const double cPT =
-                                __dsub_rn(__dsub_rn(__dsub_rn(__ldg(x + xs_ip + xs_it), cP), cT), c0);
-                            double v = __dadd_rn(c0, __dmul_rn(cT, dT));
-                            v = __dadd_rn(v, __dmul_rn(cP, dP));
-                            v = __dadd_rn(v, __dmul_rn(__dmul_rn(cPT, dT), dP));
-                            acc = __dadd_rn(acc, __dmul_rn(v, s.vmr[(k * NLAY + l) * C + c]));
+                            const double2 c0T = __ldg(cf + 2 * k), cPPT = __ldg(cf + 2 * k + 1);
+                            double v = __dadd_rn(c0T.x, __dmul_rn(c0T.y, dT));
+                            v = __dadd_rn(v, __dmul_rn(cPPT.x, dP));
+                            v = __dadd_rn(v, __dmul_rn(__dmul_rn(cPPT.y, dT), dP));
+                            acc = __dadd_rn(acc, __dmul_rn(v, s.vmr[k * NLAY * C + sb + j * C]));
                         }
-                        acc = __dmul_rn(acc, cst.numDens[l]);
-                        if (l == cst.cloud_layer) acc = __dadd_rn(acc, cst.cloud_tau);  // main.cpp:270
-                        tau[l] = acc;
+                        acc = __dmul_rn(acc, cst.numDens[r]);
+                        if (cst.cloud_row == r) acc = __dadd_rn(acc, cst.cloud_tau);  // main.cpp:270
+                        tau[j] = acc;
                     }
                     if (MODE == MODE_TAU) {
                         if (live) {
 #pragma unroll
-                            for (int l = 0; l < NLAY; ++l)
-                                a.tau_io[((size_t)(col0 + c) * nwvl + w) * NLAY + l] = tau[l];
+                            for (int j = 0; j < HALF; ++j) {
+                                const int l = h ? (NLAY - 1 - j) : j;
+                                a.tau_io[((size_t)(col0 + c) * nwvl + w) * NLAY + l] = tau[j];
+                            }
                         }
                         continue;
                     }
@@ -269,86 +292,94 @@ __global__ void __launch_bounds__(RCM_THREADS, 1) rcm_step_kernel(const StepArgs
                 // K2: Planck source B_l = k_w / (exp(c_w / T_l) - 1) (main.cpp:188-191 regrouped so that
                 // everything that depends on the wavelength alone is precomputed on the host).
                 const double pc = __ldg(a.planck_c + w), pk = __ldg(a.planck_k + w);
-                double D[NLAY + 1];  // D[l] = B_l - B_{l+1} (l<19), D[19] = B_19, D[20] = B_0
+                double D1[HALF], Dx, X0;
                 {
-                    double Bprev = pk / (exp(pc * s.invT[c]) - 1.0);
-                    D[NLAY] = Bprev;
-                    const double cs = cst.csum;
+                    double Bo[HALF];
 #pragma unroll
-                    for (int l = 1; l < NLAY; ++l) {
-                        const double Bl = pk / (exp(pc * s.invT[l * C + c]) - 1.0);
-                        D[l - 1] = Bprev - Bl;
-                        // angle-independent parts of the fluxes: sum_mu cmu * B (see the recurrences below)
-                        Ed[l - 1] = fma(cs, Bl, Ed[l - 1]);       // E_down[l]   gets csum * B_l
-                        Eu[l] = fma(cs, Bprev, Eu[l]);            // E_up[l]     gets csum * B_{l-1}
-                        Bprev = Bl;
+                    for (int j = 0; j < HALF; ++j)
+                        Bo[j] = pk / (exp_scaled(pc, s.invT[sb + j * C] * L2E64, tab_lane) - 1.0);
+                    const double Bnb = __shfl_xor_sync(0xffffffffu, Bo[HALF - 1], 1);  // partner's boundary layer
+                    const double Bs = pk / (exp_scaled(pc, s.invTs[c] * L2E64, tab_lane) - 1.0);  // main.cpp:301
+                    const double cs = cst.csum;
+                    // angle-independent parts of the fluxes: sum_mu cmu * B (see the recurrences below)
+#pragma unroll
+                    for (int j = 0; j < HALF; ++j) {
+                        const double Bnext = (j < HALF - 1) ? Bo[j + 1] : Bnb;
+                        D1[j] = Bo[j] - Bnext;
+                        E1[j] = fma(cs, Bnext, E1[j]);
+                        if (j > 0) E2[j] = fma(cs, Bo[j - 1], E2[j]);
                     }
-                    D[NLAY - 1] = Bprev;
+                    Dx = Bo[0];
+                    const double Bstart = h ? Bs : 0.0;  // down sweep starts with L=0, up sweep with B(T_surface)
+                    X0 = Bstart - Bo[0];
+                    Eu20 = fma(cs, Bstart, Eu20);  // main.cpp:302 summed over the angles (h=1 only)
                 }
-                const double Bs = pk / (exp(pc * s.invTs[c]) - 1.0);  // surface emission, main.cpp:301
-                Eu20 = fma(cst.csum, Bs, Eu20);                        // main.cpp:302 summed over the angles
-                const double V20 = Bs - D[NLAY - 1];
 
-                // K3 + K4: for every angle, transmissions t_l = exp(-tau_l/mu) and the two sweeps.
-                //   down: N_{lev+1} = L_{lev+1} - B_{lev+1} = t_lev * N_lev + (B_lev - B_{lev+1}),  N_0 = -B_0
-                //   up:   V_lev     = U_lev - B_{lev-1}     = t_lev * V_{lev+1} + (B_lev - B_{lev-1}), V_20 = B_s - B_19
-                // (algebraically the reference's L = (1-alpha) L + alpha B with alpha = 1 - t, main.cpp:307/312,
-                //  written for the deviation from the next layer's source: one FMA per layer and sweep).
-                double t[NLAY];
+                // K3 + K4.  Written for the deviation of the radiance from the source of the NEXT layer,
+                //   down: N_{lev+1} = L_{lev+1} - B_{lev+1} = t_lev N_lev + (B_lev - B_{lev+1}),    N_0  = -B_0
+                //   up:   V_lev     = U_lev - B_{lev-1}     = t_lev V_{lev+1} + (B_lev - B_{lev-1}), V_20 = B_s - B_19
+                // which is the reference's L = (1-alpha) L + alpha B, alpha = 1 - t (main.cpp:307/312), at one
+                // FMA per layer and sweep.  Lane h=0 runs the down sweep through its layers 0..9 while lane h=1
+                // runs the up sweep through 19..10; they swap the radiance at level 10 and each finishes the
+                // other's sweep through its own layers.  Both lanes execute identical code.
+                double t[HALF];
                 for (int ia = 0; ia < nang; ++ia) {
                     const double cm = cst.cmu[ia];
                     if (cst.cube[ia]) {
                         // 1/mu of this slot is three times the previous slot's: t <- t^3
 #pragma unroll
-                        for (int l = 0; l < NLAY; ++l) t[l] = t[l] * t[l] * t[l];
+                        for (int j = 0; j < HALF; ++j) t[j] = t[j] * t[j] * t[j];
                     } else {
-                        const double nim = cst.neg_inv_mu[ia];
+                        const double nim = cst.neg_inv_mu_l2e[ia];
 #pragma unroll
-                        for (int l = 0; l < NLAY; ++l) t[l] = exp_tab(tau[l] * nim, tab_lane);
+                        for (int j = 0; j < HALF; ++j) t[j] = exp_scaled(tau[j], nim, tab_lane);
                     }
-                    double N = -D[NLAY];
+                    double X = X0;
 #pragma unroll
-                    for (int l = 0; l < NLAY; ++l) {
-                        N = fma(t[l], N, D[l]);
-                        Ed[l] = fma(cm, N, Ed[l]);
+                    for (int j = 0; j < HALF; ++j) {
+                        X = fma(t[j], X, D1[j]);
+                        E1[j] = fma(cm, X, E1[j]);
                     }
-                    double V = V20;
+                    double Y = __shfl_xor_sync(0xffffffffu, X, 1);
 #pragma unroll
-                    for (int l = NLAY - 1; l >= 1; --l) {
-                        V = fma(t[l], V, -D[l - 1]);
-                        Eu[l] = fma(cm, V, Eu[l]);
+                    for (int j = HALF - 1; j >= 1; --j) {
+                        Y = fma(t[j], Y, -D1[j - 1]);
+                        E2[j] = fma(cm, Y, E2[j]);
                     }
-                    V = fma(t[0], V, D[NLAY]);
-                    Eu[0] = fma(cm, V, Eu[0]);
+                    Y = fma(t[0], Y, Dx);
+                    E2[0] = fma(cm, Y, E2[0]);
                 }
             }
             if (MODE == MODE_TAU) continue;
 
             // ---------------- K4: reduce the G wavelength groups of every column ---------------
+            constexpr int GC = G * C;
+            // E_down, levels 1..20 (staging row = level-1)
 #pragma unroll
-            for (int l = 0; l < NLAY; ++l) s.Ep[l * RCM_THREADS + tid] = Ed[l];
+            for (int j = 0; j < HALF; ++j) s.Ep[(h ? (NLAY - 1 - j) : j) * GC + g * C + c] = h ? E2[j] : E1[j];
             __syncthreads();
-            for (int i = tid; i < NLAY * C; i += RCM_THREADS) {
+            for (int i = tid; i < NLAY * C; i += NT) {
                 const int l = i / C, cc = i % C;
                 double sum = 0.0;
-                for (int gg = 0; gg < G; ++gg) sum += s.Ep[l * RCM_THREADS + gg * C + cc];
+                for (int gg = 0; gg < G; ++gg) sum += s.Ep[l * GC + gg * C + cc];
                 s.Ed[(l + 1) * C + cc] = sum;
             }
             if (tid < C) s.Ed[tid] = 0.0;  // E_down at the top of the atmosphere stays 0 (main.cpp:300)
             __syncthreads();
+            // E_up, levels 0..20
 #pragma unroll
-            for (int l = 0; l < NLAY; ++l) s.Ep[l * RCM_THREADS + tid] = Eu[l];
-            s.Ep[NLAY * RCM_THREADS + tid] = Eu20;
+            for (int j = 0; j < HALF; ++j) s.Ep[(h ? (NLAY - 1 - j) : j) * GC + g * C + c] = h ? E1[j] : E2[j];
+            if (h) s.Ep[NLAY * GC + g * C + c] = Eu20;
             __syncthreads();
-            for (int i = tid; i < NLEV * C; i += RCM_THREADS) {
+            for (int i = tid; i < NLEV * C; i += NT) {
                 const int l = i / C, cc = i % C;
                 double sum = 0.0;
-                for (int gg = 0; gg < G; ++gg) sum += s.Ep[l * RCM_THREADS + gg * C + cc];
+                for (int gg = 0; gg < G; ++gg) sum += s.Ep[l * GC + gg * C + cc];
                 s.Eu[i] = sum;
             }
             __syncthreads();
             // heating rates (main.cpp:337-341)
-            for (int i = tid; i < NLAY * C; i += RCM_THREADS) {
+            for (int i = tid; i < NLAY * C; i += NT) {
                 const int l = i / C, cc = i % C;
                 double d = s.Ed[l * C + cc] - s.Ed[(l + 1) * C + cc] + s.Eu[(l + 1) * C + cc] - s.Eu[l * C + cc];
                 if (l == NLAY - 1) d += cst.solar_irr + s.Ed[NLAY * C + cc] - s.Eu[NLAY * C + cc];
@@ -371,8 +402,8 @@ __global__ void __launch_bounds__(RCM_THREADS, 1) rcm_step_kernel(const StepArgs
                 const double dT_stat = s.dt[tid];
 #pragma unroll
                 for (int l = 0; l < NLAY; ++l)
-                    s.T[l * C + tid] += s.dE[l * C + tid] * dt * 9.80665 / (1004.0 * cst.dp * 100.0);
-                const double Tsn = s.T[(NLAY - 1) * C + tid] * cst.conv[NLAY - 1];
+                    s.T[prow(l) * C + tid] += s.dE[l * C + tid] * dt * 9.80665 / (1004.0 * cst.dp * 100.0);
+                const double Tsn = s.T[prow(NLAY - 1) * C + tid] * cst.conv[NLAY - 1];
                 s.Ts[tid] = Tsn;
                 s.dt[tid] = dt;
                 if (tid < ncl) {
@@ -390,19 +421,19 @@ __global__ void __launch_bounds__(RCM_THREADS, 1) rcm_step_kernel(const StepArgs
             __syncthreads();
             if (last) {
                 // fluxes of the last step: the tile's block of each output array is contiguous
-                for (int i = tid; i < NLEV * ncl; i += RCM_THREADS) {
+                for (int i = tid; i < NLEV * ncl; i += NT) {
                     const int cc = i / NLEV, l = i % NLEV;
                     a.E_down[(size_t)col0 * NLEV + i] = s.Ed[l * C + cc];
                     a.E_up[(size_t)col0 * NLEV + i] = s.Eu[l * C + cc];
                 }
-                for (int i = tid; i < NLAY * ncl; i += RCM_THREADS) {
+                for (int i = tid; i < NLAY * ncl; i += NT) {
                     const int cc = i / NLAY, l = i % NLAY;
                     a.dE[(size_t)col0 * NLAY + i] = s.dE[l * C + cc];
                     if (MODE == MODE_STEP) {
-                        a.Tlayer[(size_t)col0 * NLAY + i] = s.T[l * C + cc];
+                        a.Tlayer[(size_t)col0 * NLAY + i] = s.T[prow(l) * C + cc];
                         if (a.h2o_slot >= 0)
                             a.vmr[((size_t)(col0 + cc) * nact + a.h2o_slot) * NLAY + l] =
-                                s.vmr[(a.h2o_slot * NLAY + l) * C + cc];
+                                s.vmr[(a.h2o_slot * NLAY + prow(l)) * C + cc];
                     }
                 }
                 if (MODE == MODE_STEP && tid < ncl) {
@@ -411,6 +442,31 @@ __global__ void __launch_bounds__(RCM_THREADS, 1) rcm_step_kernel(const StepArgs
                 }
             }
         }
+    }
+}
+
+// Bilinear coefficients per table cell and active species, in the reference's operation order
+// (repwvl_thermal.cpp:235-238):  coef[(ip*(nt-1)+it)][w][k] = {c0, cT, cP, cPT}.
+// src is the file-order table xsec[it][species][w][ip].
+__global__ void rcm_coef_kernel(const double* __restrict__ src, double* __restrict__ dst, int nt, int ns, int nw,
+                                int np, int nact, const int* __restrict__ species) {
+    const size_t n = (size_t)(np - 1) * (nt - 1) * nw * nact;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        size_t r = i;
+        const int k = r % nact; r /= nact;
+        const int w = r % nw; r /= nw;
+        const int it = r % (nt - 1); r /= (nt - 1);
+        const int ip = (int)r;
+        const int sp = species[k];
+        auto X = [&](int b, int cc) { return src[(((size_t)b * ns + sp) * nw + w) * np + cc]; };
+        const double c0 = X(it, ip);
+        const double cT = __dsub_rn(X(it + 1, ip), c0);
+        const double cP = __dsub_rn(X(it, ip + 1), c0);
+        const double cPT = __dsub_rn(__dsub_rn(__dsub_rn(X(it + 1, ip + 1), cP), cT), c0);
+        dst[4 * i + 0] = c0;
+        dst[4 * i + 1] = cT;
+        dst[4 * i + 2] = cP;
+        dst[4 * i + 3] = cPT;
     }
 }
 
@@ -461,20 +517,6 @@ __global__ void __launch_bounds__(1024) rcm_reduce_diag_kernel(const double* __r
     }
 }
 
-// xsec[it][species][wvl][ip] (file order) -> xsec[ip][it][species][wvl] (wavelength fastest)
-__global__ void rcm_relayout_kernel(const double* __restrict__ src, double* __restrict__ dst, int nt, int ns, int nw,
-                                    int np) {
-    const size_t n = (size_t)nt * ns * nw * np;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        size_t r = i;
-        const int w = r % nw; r /= nw;
-        const int sp = r % ns; r /= ns;
-        const int it = r % nt; r /= nt;
-        const int ip = (int)r;
-        dst[i] = src[(((size_t)it * ns + sp) * nw + w) * np + ip];
-    }
-}
-
 // ------------------------------------------------------------------------------------------
 // FP64-pipe microbenchmarks: the measured denominators of the roofline.  Each
 // thread runs `iters` rounds of 8 independent dependency chains.
@@ -495,7 +537,7 @@ __global__ void __launch_bounds__(256) rcm_microbench_kernel(double* out, long i
             if (WHICH == 0) v[k] = fma(v[k], a, b);
             if (WHICH == 1) v[k] = exp(v[k]) - 1.5;
             if (WHICH == 2) v[k] = -1.0 / v[k] - 1.7;
-            if (WHICH == 3) v[k] = exp_tab(v[k], tl) - 1.5;
+            if (WHICH == 3) v[k] = exp_scaled(v[k], L2E64, tl) - 1.5;
         }
     }
     double sacc = 0;
@@ -567,28 +609,43 @@ __global__ void rcm_cplkavg_kernel(int n, const double* lo, const double* hi, co
 
 }  // namespace
 
-size_t rcm_step_smem_bytes(int C, int nactive) {
-    size_t d = (size_t)EXP_TAB * 32 + (size_t)NLAY * C * 4 + (size_t)nactive * NLAY * C + (size_t)NLEV * RCM_THREADS +
-               (size_t)NLEV * C * 2 + (size_t)C * 3;
+size_t rcm_step_smem_bytes(int C, int nactive, int nthreads) {
+    size_t d = (size_t)EXP_TAB * 32 + (size_t)NLAY * C * 4 + (size_t)nactive * NLAY * C +
+               (size_t)NLEV * (nthreads / 2) + (size_t)NLEV * C * 2 + (size_t)C * 3;
     return d * sizeof(double) + (size_t)NLAY * C * sizeof(int);
 }
 
-template <int MODE, int NACT>
+template <int MODE, int NACT, int C, int NT>
 static cudaError_t launch_t(const StepArgs& a, int nactive, int grid, cudaStream_t st) {
-    const size_t smem = rcm_step_smem_bytes(a.C, nactive);
-    cudaError_t e = cudaFuncSetAttribute(rcm_step_kernel<MODE, NACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem);
+    const size_t smem = rcm_step_smem_bytes(C, nactive, NT);
+    auto kern = rcm_step_kernel<MODE, NACT, C, NT>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    rcm_step_kernel<MODE, NACT><<<grid, RCM_THREADS, smem, st>>>(a);
+    kern<<<grid, NT, smem, st>>>(a);
     return cudaGetLastError();
 }
 
-cudaError_t rcm_launch_step(int mode, const StepArgs& a, int nactive, int grid, cudaStream_t st) {
+template <int MODE>
+static cudaError_t launch_m(const StepArgs& a, int nactive, int grid, cudaStream_t st) {
     const bool five = (nactive == 5);
+    if (a.C == 64 && a.nthreads == 512)
+        return five ? launch_t<MODE, 5, 64, 512>(a, nactive, grid, st) : launch_t<MODE, 0, 64, 512>(a, nactive, grid, st);
+    if (a.C == 32 && a.nthreads == 256)
+        return five ? launch_t<MODE, 5, 32, 256>(a, nactive, grid, st) : launch_t<MODE, 0, 32, 256>(a, nactive, grid, st);
+    if (a.C == 64 && a.nthreads == 384)
+        return five ? launch_t<MODE, 5, 64, 384>(a, nactive, grid, st) : launch_t<MODE, 0, 64, 384>(a, nactive, grid, st);
+    if (a.C == 32 && a.nthreads == 192)
+        return five ? launch_t<MODE, 5, 32, 192>(a, nactive, grid, st) : launch_t<MODE, 0, 32, 192>(a, nactive, grid, st);
+    if (a.C == 16 && a.nthreads == 512)
+        return five ? launch_t<MODE, 5, 16, 512>(a, nactive, grid, st) : launch_t<MODE, 0, 16, 512>(a, nactive, grid, st);
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t rcm_launch_step(int mode, const StepArgs& a, int nactive, int grid, cudaStream_t st) {
     switch (mode) {
-        case MODE_STEP: return five ? launch_t<MODE_STEP, 5>(a, nactive, grid, st) : launch_t<MODE_STEP, 0>(a, nactive, grid, st);
-        case MODE_TAU: return five ? launch_t<MODE_TAU, 5>(a, nactive, grid, st) : launch_t<MODE_TAU, 0>(a, nactive, grid, st);
-        case MODE_RT: return five ? launch_t<MODE_RT, 5>(a, nactive, grid, st) : launch_t<MODE_RT, 0>(a, nactive, grid, st);
+        case MODE_STEP: return launch_m<MODE_STEP>(a, nactive, grid, st);
+        case MODE_TAU: return launch_m<MODE_TAU>(a, nactive, grid, st);
+        case MODE_RT: return launch_m<MODE_RT>(a, nactive, grid, st);
     }
     return cudaErrorInvalidValue;
 }
@@ -599,9 +656,9 @@ cudaError_t rcm_launch_reduce_diag(const double* diag, int nsteps, int ncol, dou
     return cudaGetLastError();
 }
 
-cudaError_t rcm_launch_relayout(const double* xsec_file, double* xsec_dev, int nt, int ns, int nw, int np,
-                                cudaStream_t st) {
-    rcm_relayout_kernel<<<296, 256, 0, st>>>(xsec_file, xsec_dev, nt, ns, nw, np);
+cudaError_t rcm_launch_coef(const double* xsec_file, double* coef, int nt, int ns, int nw, int np, int nact,
+                            const int* d_species, cudaStream_t st) {
+    rcm_coef_kernel<<<296, 256, 0, st>>>(xsec_file, coef, nt, ns, nw, np, nact, d_species);
     return cudaGetLastError();
 }
 

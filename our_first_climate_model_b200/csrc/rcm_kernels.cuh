@@ -10,7 +10,8 @@ constexpr int NLAY = RCM_NLAYER;
 constexpr int NLEV = RCM_NLEVEL;
 constexpr int MAX_ANGLE = 64;
 constexpr int MAX_TPERT = 16;
-constexpr int RCM_THREADS = 256;   // threads per CTA of the step kernel (2 warps per SM sub-partition)
+constexpr int RCM_THREADS = 512;   // threads per CTA of the step kernel (4 warps per SM sub-partition)
+constexpr int HALF = NLAY / 2;     // layers owned by each lane of a pair
 constexpr int EXP_TAB = 64;        // entries of the 2^(j/64) table used by the solver's exp
 
 // Everything that is uniform over the ensemble.  Lives in __constant__ memory.
@@ -19,14 +20,17 @@ struct DevConst {
     int species[RCM_NSPECIES];  // active species, ascending
     int cloud_layer;
     double cloud_tau, dp, max_dT, dt_cap, solar_irr, dT_converged;
-    // per layer (top-down index l), from the shared pressure grid - host computed with the
-    // reference's expressions (repwvl_thermal.cpp:202, :214, :226, :240)
+    // per layer, from the shared pressure grid - host computed with the reference's expressions
+    // (repwvl_thermal.cpp:202, :214, :226, :240).  ip/player/conv are indexed by the top-down layer l;
+    // ipcell/delP/numDens/tref_ip by the pair-order row (l for l<10, 29-l otherwise).
     int ip[NLAY];
+    int ipcell[NLAY];  // ip * (n_tpert-1): first table cell of the layer's pressure interval
+    int cloud_row;     // pair-order row of the cloud layer, -1 if none
     double delP[NLAY], numDens[NLAY], tref_ip[NLAY], player[NLAY], conv[NLAY];
     double t_pert[MAX_TPERT];
     // angle schedule: slot a holds quadrature node n_a (1/mu = 2*nangle/n_a ... see capi) either
     // evaluated with exp (head) or derived by cubing the transmissions of the previous slot
-    double neg_inv_mu[MAX_ANGLE];  // -1/mu of the slot
+    double neg_inv_mu_l2e[MAX_ANGLE];  // -1/mu of the slot, times 64/ln2 (argument scaling of exp_scaled)
     double cmu[MAX_ANGLE];         // 2*pi*mu*dmu of the slot
     int cube[MAX_ANGLE];           // 1: t <- t^3 from the previous slot, 0: exp
     double csum;                   // sum of cmu
@@ -36,12 +40,15 @@ struct DevConst {
 // Per-launch arguments (pointers into the solver's device allocations).
 struct StepArgs {
     int ncol;            // columns in this launch
-    int C;               // columns per tile (RCM_THREADS % C == 0)
+    int C;               // columns per tile
+    int nthreads;        // threads per CTA (2 * C * wavelength groups)
+    int stagger_mode;    // 0: odd wavelength groups start late every tile-step, 1: odd CTAs start late once
+    long long stagger_cycles;
     int ntiles;
     int nsteps;          // time steps fused in this launch
     long step_index;     // global index of the first step (0 => initial-profile tau, main.cpp:500-504)
-    // table, re-laid out as xsec[ip][it][species][wvl]
-    const double* __restrict__ xsec;
+    // table as bilinear coefficients coef[cell][wvl][active species][4]
+    const double* __restrict__ coef;
     const double* __restrict__ planck_c;  // [nwvl] h*c/(lambda*kB)   [K]
     const double* __restrict__ planck_k;  // [nwvl] weight*2*h*c^2/lambda^5/1e9
     // column state
@@ -66,13 +73,13 @@ struct StepArgs {
 
 enum { MODE_STEP = 0, MODE_TAU = 1, MODE_RT = 2 };
 
-size_t rcm_step_smem_bytes(int C, int nactive);
+size_t rcm_step_smem_bytes(int C, int nactive, int nthreads);
 cudaError_t rcm_upload_const(const DevConst& c);
 cudaError_t rcm_launch_step(int mode, const StepArgs& a, int nactive, int grid, cudaStream_t st);
 cudaError_t rcm_launch_reduce_diag(const double* diag, int nsteps, int ncol, double dT_converged, double* scalars,
                                    cudaStream_t st);
-cudaError_t rcm_launch_relayout(const double* xsec_file, double* xsec_dev, int nt, int ns, int nw, int np,
-                                cudaStream_t st);
+cudaError_t rcm_launch_coef(const double* xsec_file, double* coef, int nt, int ns, int nw, int np, int nact,
+                            const int* d_species, cudaStream_t st);
 cudaError_t rcm_launch_microbench(int which, double* out, const double* tab, long iters, int grid,
                                   cudaStream_t st);
 cudaError_t rcm_launch_cplkavg(int n, const double* lo, const double* hi, const double* t, double* out,

@@ -1,0 +1,170 @@
+"""Host side of the drop-in boundary (no GPU): the C-ABI library, loaders, initialisation."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, table_path
+from oracle import refcpu as R
+
+REF = "/root/reference"
+needs_refsrc = pytest.mark.skipif(not os.path.isdir(REF), reason="/root/reference not mounted")
+needs_ref = pytest.mark.skipif(not R.available(), reason="oracle/_ref not built")
+
+
+def test_library_loads_and_exports_every_declared_symbol(rcm):
+    lib = rcm.load_library()
+    assert len(rcm.DECLARED_SYMBOLS) >= 35
+    missing = [s for s in rcm.DECLARED_SYMBOLS if not hasattr(lib, s)]
+    assert not missing, missing
+    # and nothing torch-typed in the boundary: the header is plain C
+    subprocess.check_call(["gcc", "-std=c99", "-fsyntax-only", "-x", "c", os.path.join(ROOT, "include", "rcm_b200.h")])
+
+
+def test_no_cpu_fallback(rcm):
+    if rcm.device_count() > 0:
+        pytest.skip("GPU present")
+    with pytest.raises(rcm.RcmError, match="no CUDA device"):
+        rcm.Solver(0)
+
+
+def test_product_never_imports_the_oracle():
+    """The shipped path must not route through the CPU oracle (or any CPU fallback)."""
+    import re
+    pkg = os.path.join(ROOT, "our_first_climate_model_b200")
+    pat = re.compile(r"(from|import)\s+oracle|oracle[/\\.](port|refcpu|rcm_oracle|_ref)|liboracle|libref_oracle|rcmo_")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")) or f == "Makefile":
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                assert not pat.search(txt), f"{f} references the oracle"
+
+
+def test_table_loader_rcmtab(rcm, port):
+    for n in (10, 20, 100):
+        t = rcm.Table(table_path(n))
+        ref = port.load_rcmtab(table_path(n))
+        assert (t.n_tpert, t.n_species, t.n_wvl, t.n_p) == (9, 9, n, 41)
+        for nm in ("xsec", "wvl", "weight", "p_grid", "t_ref", "t_pert", "vmrs_ref"):
+            assert np.array_equal(getattr(t, nm), ref[nm]), nm
+    t = rcm.Table(table_path(100))
+    assert t.p_grid[0] == 110000.0 and t.p_grid[0] > t.p_grid[-1]          # descending
+    assert list(t.t_pert) == [-120, -70, -40, -20, 0, 20, 40, 70, 120]
+    assert t.weight.min() < 0 < t.weight.max()                              # signed weights
+
+
+@needs_refsrc
+def test_table_loader_netcdf4_subset(rcm):
+    """The C++ HDF5-subset reader on the reference's own .nc files == the independent Python reader."""
+    for n in (10, 20, 100):
+        a = rcm.Table(f"{REF}/repwvl_V2.01_cpp/Reduced{n}Forcing.nc")
+        b = rcm.Table(table_path(n))
+        for nm in ("xsec", "wvl", "weight", "p_grid", "t_ref", "t_pert", "vmrs_ref"):
+            assert np.array_equal(getattr(a, nm), getattr(b, nm)), nm
+
+
+def test_table_loader_errors(rcm, tmp_path):
+    with pytest.raises(rcm.RcmError, match="not found"):
+        rcm.Table(str(tmp_path / "missing.nc"))
+    bad = tmp_path / "bad.nc"
+    bad.write_bytes(b"\x89HDF\r\n\x1a\n" + b"\0" * 200)
+    with pytest.raises(rcm.RcmError, match="format"):
+        rcm.Table(str(bad))
+    trunc = tmp_path / "trunc.rcmtab"
+    trunc.write_bytes(open(table_path(10), "rb").read()[:5000])
+    with pytest.raises(rcm.RcmError, match="format"):
+        rcm.Table(str(trunc))
+
+
+def test_atm_reader(rcm):
+    a = rcm.read_atm(os.path.join(GOLDEN, "column21.atm"))
+    assert a.shape == (21, 9)
+    assert a[0, 1] == 0 and a[-1, 1] == 1000 and a[-1, 2] == 288.2 and a[0, 4] == 5.246 and a[5, 8] == 0.315
+    b = rcm.read_atm(os.path.join(GOLDEN, "column21.lbl.atm"))
+    assert b.shape == (21, 6) and np.array_equal(a[:, :6], b)
+    if os.path.isdir(REF):
+        assert np.array_equal(rcm.read_atm(f"{REF}/repwvl_V2.01_cpp/test.atm"), a)
+
+
+def test_init_columns_and_solar_match_oracle_bitwise(rcm, port, golden):
+    g = golden
+    a = rcm.init_columns(g["plevel"], g["Tlevel"], g["vmr_ppm_level"], 1.0)
+    b = port.init_columns(g["plevel"], g["Tlevel"], g["vmr_ppm_level"], 1.0)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(a["Tlayer"], g["init_Tlayer"]) and np.array_equal(a["rel_hum"], g["init_rel_hum"])
+    a2 = rcm.init_columns(g["plevel"], g["Tlevel"][:2], g["vmr_ppm_level"][:2], 2.0)   # 2xCO2 (main.cpp:452-456)
+    assert np.array_equal(a2["vmr9"][:, 1], 2.0 * 1e-6 * 400 * np.ones((2, 20)))
+    assert rcm.solar_setup()["solar_irr"] == float(g["solar_irr"])
+    p = rcm.default_params()
+    assert (p.nangle, p.cloud_layer, p.cloud_tau, p.dp, p.max_dT, p.dt_cap, p.species_mask) == (30, 17, 1.0, 50.0, 5.0,
+                                                                                               43200.0, 0x2F)
+
+
+def test_lowerpos_edge_semantics(rcm, golden_misc, port):
+    asc, desc = [0.0, 1.0, 2.0, 3.0], [3.0, 2.0, 1.0, 0.0]
+    assert [rcm.lowerpos(asc, x) for x in golden_misc["lp_x"]] == list(golden_misc["lp_asc"])
+    assert [rcm.lowerpos(desc, x) for x in golden_misc["lp_x"]] == list(golden_misc["lp_desc"])
+    rng = np.random.default_rng(0)
+    t = rcm.Table(table_path(100))
+    for x in rng.uniform(-100, 2e5, 300):
+        assert rcm.lowerpos(t.p_grid, x) == port.lowerpos(t.p_grid, x)
+
+
+def test_ensemble_is_deterministic_and_member0_is_the_base_column(rcm, golden):
+    pl, bT, bv = golden["plevel"], golden["Tlevel"][0], golden["vmr_ppm_level"][0]
+    T1, v1 = rcm.make_ensemble(14, 12345, pl, bT, bv)
+    assert np.array_equal(T1, golden["Tlevel"]) and np.array_equal(v1, golden["vmr_ppm_level"])
+    assert np.array_equal(T1[0], bT) and np.array_equal(v1[0], bv)
+    T2, _ = rcm.make_ensemble(200, 7, pl, bT, bv)
+    assert np.abs(T2 - bT).max() < 20 and np.abs(T2[1:] - bT).min(axis=1).max() > 0
+    Ta, _ = rcm.make_ensemble(50, 7, pl, bT, bv)
+    assert np.array_equal(Ta, T2[:50])  # a shard of a bigger ensemble is the same columns
+
+
+def _write(path, text):
+    with open(path, "w") as f:
+        f.write(text)
+    return str(path)
+
+
+def test_ascii_reader_semantics(rcm, tmp_path):
+    p = _write(tmp_path / "a.asc", "# comment\n% another\n\n 4000.5 1e-3 2e-3   3e-3\n\t5000 0.1 0.2 0.3 # trailing\n"
+                                   "6000 x 0.5 1.5e2\n")
+    st, x, y = rcm.ascii_file2xy2D(p)
+    assert st == 0 and list(x) == [4000.5, 5000.0, 6000.0]
+    assert np.array_equal(y, [[1e-3, 2e-3, 3e-3], [0.1, 0.2, 0.3], [0.0, 0.5, 150.0]])   # non-numeric -> 0
+    assert rcm.ascii_file2xy2D(str(tmp_path / "nope.asc"))[0] == -1                       # ASCIIFILE_NOT_FOUND
+    assert rcm.ascii_file2xy2D(_write(tmp_path / "r.asc", "1 2 3\n4 5\n"))[0] == -5       # NOT_A_RECTANGULAR_MATRIX
+    assert rcm.ascii_file2xy2D(_write(tmp_path / "e.asc", "# only comments\n\n"))[0] == -5  # empty: min != max
+
+
+@needs_ref
+def test_ascii_reader_equals_reference_reader(rcm, tmp_path):
+    rng = np.random.default_rng(3)
+    nw = 500
+    wvl = np.sort(rng.uniform(4000, 1e5, nw))
+    tau = 10 ** rng.uniform(-8, 3, (nw, 20))
+    lines = ["# wavelength[nm] dtau(20 layers, top-down)  (lbl.arts/README format)"]
+    for i in range(nw):
+        sep = "\t" if i % 3 == 0 else " "
+        lines.append(sep.join([f"{wvl[i]:.6f}"] + [f"{v:.9e}" for v in tau[i]]) + ("   " if i % 5 == 0 else ""))
+        if i % 97 == 0:
+            lines.append("")
+            lines.append("% block comment")
+    p = _write(tmp_path / "lbl.co2.asc", "\n".join(lines) + "\n")
+    st1, x1, y1 = R.ascii_file2xy2D(p)
+    st2, x2, y2 = rcm.ascii_file2xy2D(p)
+    assert st1 == st2 == 0 and np.array_equal(x1, x2) and np.array_equal(y1, y2) and y2.shape == (nw, 20)
+    for bad in ("1 2 3\n4 5\n", "", "#x\n"):
+        pb = _write(tmp_path / "bad.asc", bad)
+        assert R.ascii_file2xy2D(pb)[0] == rcm.ascii_file2xy2D(pb)[0]
+
+
+def test_cplkavg_host_matches_reference_samples(rcm, golden_misc):
+    m = golden_misc
+    got = np.array([rcm.cplkavg_host(a, b, t)[0] for a, b, t in zip(m["cpl_lo"], m["cpl_hi"], m["cpl_T"])])
+    assert np.array_equal(got, m["cpl_val"])
+    assert rcm.cplkavg_host(500.0, 400.0, 300.0)[1] == 1
