@@ -1,6 +1,7 @@
 // C ABI of the solver (include/rcm_b200.h): handle management, host-side precomputation of
 // everything that depends only on the shared pressure grid / wavelength table, uploads,
 // launches and downloads.  No CPU fallback: without a CUDA device rcm_create() fails.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -21,7 +22,7 @@ struct rcm_solver {
     DevConst dc{};
     bool const_dirty = true;
     int opt_angle_cubes = 1;
-    int opt_config = 1;        // 0: 512 threads x 64 columns, 1: 256 threads x 32 columns (2 CTAs/SM), 2: 384x64, 3: 192x32
+    int opt_config = 3;        // 0: 512 threads x 64 columns, 1: 256 threads x 32 columns (2 CTAs/SM), 2: 384x64, 3: 192x32
     int opt_stagger = 0;       // de-phasing delay in cycles (0 = off)
     // table
     bool has_table = false;
@@ -93,38 +94,53 @@ void build_angles(rcm_solver* s) {
     const int na = s->p.nangle;
     const double dmu = 1.0 / (double)na;
     d.nangle = na;
-    std::vector<int> order;
-    std::vector<int> cube;
+    // chains of node indices: head first, then the nodes reached by successive cubes
+    std::vector<std::vector<int>> chains;
     if (s->opt_angle_cubes) {
         std::vector<char> used(na, 0);
         for (int i = na - 1; i >= 0; --i) {
             if (used[i]) continue;
+            std::vector<int> ch;
             int n = 2 * i + 1;
-            bool head = true;
             while (true) {
                 const int idx = (n - 1) / 2;
                 used[idx] = 1;
-                order.push_back(idx);
-                cube.push_back(head ? 0 : 1);
-                head = false;
+                ch.push_back(idx);
                 if (n % 3 != 0) break;
                 n /= 3;
             }
+            chains.push_back(ch);
         }
     } else {
-        for (int i = 0; i < na; ++i) {
-            order.push_back(i);
-            cube.push_back(0);
+        for (int i = 0; i < na; ++i) chains.push_back({i});
+    }
+    // deal the chains to the two streams, longest first, always to the shorter stream
+    std::stable_sort(chains.begin(), chains.end(),
+                     [](const std::vector<int>& a, const std::vector<int>& b) { return a.size() > b.size(); });
+    std::vector<int> order[2], cube[2];
+    for (const auto& ch : chains) {
+        const int k = order[1].size() < order[0].size() ? 1 : 0;
+        for (size_t m = 0; m < ch.size(); ++m) {
+            order[k].push_back(ch[m]);
+            cube[k].push_back(m ? 1 : 0);
         }
     }
+    d.nslot = (int)std::max(order[0].size(), order[1].size());
     double sum = 0.0;
-    for (int a = 0; a < na; ++a) {
-        const double mu = dmu / 2.0 + dmu * (double)order[a];
-        d.neg_inv_mu_l2e[a] = (-1.0 / mu) * 92.33248261689366;  // times 64/ln2, see exp_scaled
-        d.cmu[a] = 2 * M_PI * mu * dmu;
-        d.cube[a] = cube[a];
-        sum += d.cmu[a];
-    }
+    for (int k = 0; k < 2; ++k)
+        for (int a = 0; a < d.nslot; ++a) {
+            if (a < (int)order[k].size()) {
+                const double mu = dmu / 2.0 + dmu * (double)order[k][a];  // main.cpp:482
+                d.neg_inv_mu_l2e[k][a] = (-1.0 / mu) * 92.33248261689366;  // times 64/ln2, see exp_scaled
+                d.cmu[k][a] = 2 * M_PI * mu * dmu;
+                d.cube[k][a] = cube[k][a];
+                sum += d.cmu[k][a];
+            } else {  // padding slot: exp(0) = 1 with zero quadrature weight
+                d.neg_inv_mu_l2e[k][a] = 0.0;
+                d.cmu[k][a] = 0.0;
+                d.cube[k][a] = 0;
+            }
+        }
     d.csum = sum;
 }
 
@@ -220,11 +236,16 @@ int ensure_tau(rcm_solver* s) {
     return RCM_OK;
 }
 
-// Columns per tile: 64 when that still gives every SM a tile (and shared memory allows), else 16.
-int pick_C(const rcm_solver* s, int ncol, int nsm) {
-    if ((ncol + 63) / 64 >= nsm && rcm_step_smem_bytes(64, s->nactive, 512) <= 227 * 1024)
-        return (s->opt_config == 1 || s->opt_config == 3) ? 32 : 64;
-    return 16;
+// CTA shapes (columns per tile, threads, resident CTAs per SM).  Several small independent CTAs per SM
+// de-phase the latency-bound table phase of one CTA against the issue-bound angle loop of another.
+struct CtaShape { int C, nthreads, per_sm; };
+CtaShape pick_shape(const rcm_solver* s, int ncol, int nsm) {
+    static const CtaShape shapes[] = {{64, 512, 1}, {32, 256, 2}, {64, 384, 1}, {32, 192, 2}, {16, 128, 3}, {16, 96, 4}};
+    CtaShape sh = shapes[(s->opt_config >= 0 && s->opt_config < 6) ? s->opt_config : 3];
+    // small ensembles: more, smaller tiles so that every SM gets work
+    if ((ncol + sh.C - 1) / sh.C < nsm * sh.per_sm && sh.C > 16) sh = shapes[4];
+    if (rcm_step_smem_bytes(sh.C, s->nactive, sh.nthreads) * sh.per_sm > 227 * 1024) sh.per_sm = 1;
+    return sh;
 }
 
 int launch(rcm_solver* s, int mode, int nsteps, bool want_diag) {
@@ -236,10 +257,11 @@ int launch(rcm_solver* s, int mode, int nsteps, bool want_diag) {
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, s->device);
     StepArgs a{};
     a.ncol = s->ncol;
-    a.C = pick_C(s, s->ncol, nsm);
+    const CtaShape sh = pick_shape(s, s->ncol, nsm);
+    a.C = sh.C;
     a.ntiles = (s->ncol + a.C - 1) / a.C;
-    a.nthreads = (a.C == 32) ? (s->opt_config == 3 ? 192 : 256) : ((a.C == 64 && s->opt_config == 2) ? 384 : 512);
-    a.stagger_mode = (a.C == 32) ? 1 : 0;
+    a.nthreads = sh.nthreads;
+    a.stagger_mode = (sh.per_sm > 1) ? 1 : 0;
     a.stagger_cycles = s->opt_stagger;
     a.nsteps = nsteps;
     a.step_index = s->step_index;
@@ -261,7 +283,7 @@ int launch(rcm_solver* s, int mode, int nsteps, bool want_diag) {
     a.lowpos_t = s->d_lowpos;
     a.exp_tab = s->d_exp_tab;
     a.h2o_slot = s->h2o_slot;
-    const int ctas = nsm * (a.nthreads <= 256 ? 2 : 1);
+    const int ctas = nsm * sh.per_sm;
     const int grid = a.ntiles < ctas ? a.ntiles : ctas;
     std::pair<cudaEvent_t, cudaEvent_t> ev;
     if (!s->ev_free.empty()) {

@@ -57,6 +57,20 @@ __device__ __forceinline__ double exp_scaled(double a, double b_l2e64, const dou
 
 constexpr double L2E64 = 0x1.71547652b82fep+6;  // 64/ln2
 
+// a / d for normal, finite d: hardware reciprocal seed (20 bits) + two Newton steps + one residual
+// correction of the quotient (<= 1 ulp).  7 FP64-pipe instructions, no special-case branches
+// (the IEEE division routine costs ~45 instructions with its slow-path checks).
+__device__ __forceinline__ double div_fast(double a, double d) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    const double q = a * r;
+    return fma(fma(-d, q, a), r, q);
+}
+
 // descending compare-exchange
 __device__ __forceinline__ void cex(double& a, double& b) {
     const double hi = fmax(a, b), lo = fmin(a, b);
@@ -135,7 +149,7 @@ __device__ __forceinline__ void prep_tau_indices(const Smem<C, NT>& s, int tid) 
 }
 
 template <int MODE, int NACT, int C, int NT>
-__global__ void __launch_bounds__(NT, 512 / NT) rcm_step_kernel(const StepArgs a) {
+__global__ void __launch_bounds__(NT, (NT == 256 || NT == 512) ? 512 / NT : 384 / NT) rcm_step_kernel(const StepArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int G = NT / (2 * C);  // wavelength groups
     const int tid = threadIdx.x, lane = tid & 31;
@@ -146,7 +160,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcm_step_kernel(const StepArgs a
 
     for (int i = tid; i < EXP_TAB * 32; i += NT) s.exp_tab[i] = a.exp_tab[i >> 5];
     const double* tab_lane = s.exp_tab + lane;
-    const int nang = cst.nangle, nwvl = cst.nwvl;
+    const int nslot = cst.nslot, nwvl = cst.nwvl;
 
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
         const int col0 = tile * C;
@@ -230,8 +244,12 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcm_step_kernel(const StepArgs a
             // E1[j]: flux of the first sweep  (h=0: E_down[j+1],   h=1: E_up[19-j])
             // E2[j]: flux of the second sweep (h=0: E_up[j],       h=1: E_down[20-j])
             double E1[HALF], E2[HALF], Eu20 = 0.0;
+            int coff[HALF];  // offset (in double2) of this column's table cell per owned layer: independent of w
 #pragma unroll
-            for (int j = 0; j < HALF; ++j) E1[j] = E2[j] = 0.0;
+            for (int j = 0; j < HALF; ++j) {
+                E1[j] = E2[j] = 0.0;
+                coff[j] = (MODE == MODE_RT) ? 0 : (cst.ipcell[h * HALF + j] + s.it[sb + j * C]) * nwvl * 2 * nact;
+            }
 
             if (MODE == MODE_STEP && a.stagger_cycles > 0) {
                 // De-phase the warps: every second wavelength group (or CTA) starts half an item later, so its
@@ -259,10 +277,8 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcm_step_kernel(const StepArgs a
 #pragma unroll
                     for (int j = 0; j < HALF; ++j) {
                         const int r = h * HALF + j;
-                        const int it = s.it[sb + j * C];
                         const double dT = s.delT[sb + j * C], dP = cst.delP[r];
-                        const double2* cf = reinterpret_cast<const double2*>(a.coef) +
-                                            ((size_t)(cst.ipcell[r] + it) * nwvl + w) * (2 * nact);
+                        const double2* cf = reinterpret_cast<const double2*>(a.coef) + (coff[j] + w * 2 * nact);
                         double acc = 0.0;
 #pragma unroll
                         for (int k = 0; k < (NACT > 0 ? NACT : RCM_NSPECIES); ++k) {
@@ -297,9 +313,9 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcm_step_kernel(const StepArgs a
                     double Bo[HALF];
 #pragma unroll
                     for (int j = 0; j < HALF; ++j)
-                        Bo[j] = pk / (exp_scaled(pc, s.invT[sb + j * C] * L2E64, tab_lane) - 1.0);
+                        Bo[j] = div_fast(pk, exp_scaled(pc, s.invT[sb + j * C] * L2E64, tab_lane) - 1.0);
                     const double Bnb = __shfl_xor_sync(0xffffffffu, Bo[HALF - 1], 1);  // partner's boundary layer
-                    const double Bs = pk / (exp_scaled(pc, s.invTs[c] * L2E64, tab_lane) - 1.0);  // main.cpp:301
+                    const double Bs = div_fast(pk, exp_scaled(pc, s.invTs[c] * L2E64, tab_lane) - 1.0);  // main.cpp:301
                     const double cs = cst.csum;
                     // angle-independent parts of the fluxes: sum_mu cmu * B (see the recurrences below)
 #pragma unroll
@@ -322,32 +338,59 @@ __global__ void __launch_bounds__(NT, 512 / NT) rcm_step_kernel(const StepArgs a
                 // FMA per layer and sweep.  Lane h=0 runs the down sweep through its layers 0..9 while lane h=1
                 // runs the up sweep through 19..10; they swap the radiance at level 10 and each finishes the
                 // other's sweep through its own layers.  Both lanes execute identical code.
-                double t[HALF];
-                for (int ia = 0; ia < nang; ++ia) {
-                    const double cm = cst.cmu[ia];
-                    if (cst.cube[ia]) {
-                        // 1/mu of this slot is three times the previous slot's: t <- t^3
+                // Two angles are carried at once (streams A and B of the schedule): their dependency chains are
+                // independent, which doubles the instruction-level parallelism of the sweeps.
+                double tA[HALF], tB[HALF];
+                for (int is = 0; is < nslot; ++is) {
+                    const double cmA = cst.cmu[0][is], cmB = cst.cmu[1][is];
+                    const int kind = cst.cube[0][is] | (cst.cube[1][is] << 1);
+                    const double nimA = cst.neg_inv_mu_l2e[0][is], nimB = cst.neg_inv_mu_l2e[1][is];
+                    if (kind == 0) {
 #pragma unroll
-                        for (int j = 0; j < HALF; ++j) t[j] = t[j] * t[j] * t[j];
+                        for (int j = 0; j < HALF; ++j) {
+                            tA[j] = exp_scaled(tau[j], nimA, tab_lane);
+                            tB[j] = exp_scaled(tau[j], nimB, tab_lane);
+                        }
+                    } else if (kind == 1) {  // 1/mu of slot A is three times its previous slot's: t <- t^3
+#pragma unroll
+                        for (int j = 0; j < HALF; ++j) {
+                            tA[j] = tA[j] * tA[j] * tA[j];
+                            tB[j] = exp_scaled(tau[j], nimB, tab_lane);
+                        }
+                    } else if (kind == 2) {
+#pragma unroll
+                        for (int j = 0; j < HALF; ++j) {
+                            tA[j] = exp_scaled(tau[j], nimA, tab_lane);
+                            tB[j] = tB[j] * tB[j] * tB[j];
+                        }
                     } else {
-                        const double nim = cst.neg_inv_mu_l2e[ia];
 #pragma unroll
-                        for (int j = 0; j < HALF; ++j) t[j] = exp_scaled(tau[j], nim, tab_lane);
+                        for (int j = 0; j < HALF; ++j) {
+                            tA[j] = tA[j] * tA[j] * tA[j];
+                            tB[j] = tB[j] * tB[j] * tB[j];
+                        }
                     }
-                    double X = X0;
+                    double XA = X0, XB = X0;
 #pragma unroll
                     for (int j = 0; j < HALF; ++j) {
-                        X = fma(t[j], X, D1[j]);
-                        E1[j] = fma(cm, X, E1[j]);
+                        XA = fma(tA[j], XA, D1[j]);
+                        XB = fma(tB[j], XB, D1[j]);
+                        E1[j] = fma(cmA, XA, E1[j]);
+                        E1[j] = fma(cmB, XB, E1[j]);
                     }
-                    double Y = __shfl_xor_sync(0xffffffffu, X, 1);
+                    double YA = __shfl_xor_sync(0xffffffffu, XA, 1);
+                    double YB = __shfl_xor_sync(0xffffffffu, XB, 1);
 #pragma unroll
                     for (int j = HALF - 1; j >= 1; --j) {
-                        Y = fma(t[j], Y, -D1[j - 1]);
-                        E2[j] = fma(cm, Y, E2[j]);
+                        YA = fma(tA[j], YA, -D1[j - 1]);
+                        YB = fma(tB[j], YB, -D1[j - 1]);
+                        E2[j] = fma(cmA, YA, E2[j]);
+                        E2[j] = fma(cmB, YB, E2[j]);
                     }
-                    Y = fma(t[0], Y, Dx);
-                    E2[0] = fma(cm, Y, E2[0]);
+                    YA = fma(tA[0], YA, Dx);
+                    YB = fma(tB[0], YB, Dx);
+                    E2[0] = fma(cmA, YA, E2[0]);
+                    E2[0] = fma(cmB, YB, E2[0]);
                 }
             }
             if (MODE == MODE_TAU) continue;
@@ -636,6 +679,10 @@ static cudaError_t launch_m(const StepArgs& a, int nactive, int grid, cudaStream
         return five ? launch_t<MODE, 5, 64, 384>(a, nactive, grid, st) : launch_t<MODE, 0, 64, 384>(a, nactive, grid, st);
     if (a.C == 32 && a.nthreads == 192)
         return five ? launch_t<MODE, 5, 32, 192>(a, nactive, grid, st) : launch_t<MODE, 0, 32, 192>(a, nactive, grid, st);
+    if (a.C == 16 && a.nthreads == 128)
+        return five ? launch_t<MODE, 5, 16, 128>(a, nactive, grid, st) : launch_t<MODE, 0, 16, 128>(a, nactive, grid, st);
+    if (a.C == 16 && a.nthreads == 96)
+        return five ? launch_t<MODE, 5, 16, 96>(a, nactive, grid, st) : launch_t<MODE, 0, 16, 96>(a, nactive, grid, st);
     if (a.C == 16 && a.nthreads == 512)
         return five ? launch_t<MODE, 5, 16, 512>(a, nactive, grid, st) : launch_t<MODE, 0, 16, 512>(a, nactive, grid, st);
     return cudaErrorInvalidValue;

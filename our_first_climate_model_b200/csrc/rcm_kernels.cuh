@@ -30,10 +30,12 @@ struct DevConst {
     double t_pert[MAX_TPERT];
     // angle schedule: slot a holds quadrature node n_a (1/mu = 2*nangle/n_a ... see capi) either
     // evaluated with exp (head) or derived by cubing the transmissions of the previous slot
-    double neg_inv_mu_l2e[MAX_ANGLE];  // -1/mu of the slot, times 64/ln2 (argument scaling of exp_scaled)
-    double cmu[MAX_ANGLE];         // 2*pi*mu*dmu of the slot
-    int cube[MAX_ANGLE];           // 1: t <- t^3 from the previous slot, 0: exp
-    double csum;                   // sum of cmu
+    // The nodes are dealt to two streams that the kernel advances together (nslot slots each).
+    int nslot;
+    double neg_inv_mu_l2e[2][MAX_ANGLE / 2];  // -1/mu of the slot, times 64/ln2 (argument scaling of exp_scaled)
+    double cmu[2][MAX_ANGLE / 2];             // 2*pi*mu*dmu of the slot (0 for a padding slot)
+    int cube[2][MAX_ANGLE / 2];               // 1: t <- t^3 from the stream's previous slot, 0: exp
+    double csum;                              // sum of cmu over all nodes
     // LBL band edges etc. live in global memory
 };
 

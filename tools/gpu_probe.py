@@ -17,7 +17,7 @@ Tlev, vlev = rcm.make_ensemble(ncol, 12345, pl, atm[:, 2], atm[:, 4:9].T.copy())
 st0 = rcm.init_columns(pl, Tlev, vlev)
 s.set_repwvl_table_from(rcm.Table(os.path.join(G, f"Reduced{nw}Forcing.rcmtab")))
 import itertools
-for cfg, stag in [(0,0),(1,0),(2,0),(3,0)]:
+for cfg, stag in [(3,0),(4,0),(5,0)]:
     cubes=1
     s.set_option(1, cfg); s.set_option(2, stag)
     s.set_columns(pl, st0["Tlayer"], np.full(ncol, 288.2), st0["vmr9"], st0["rel_hum"])
