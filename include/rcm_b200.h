@@ -136,10 +136,20 @@ int rcm_set_repwvl_table(rcm_solver* s, const double* xsec, const double* wvl, c
                          int n_species, int n_wvl, int n_p);
 int rcm_set_repwvl_table_from(rcm_solver* s, const rcm_table* t);
 
-/* Upload line-by-line tables (lbl.arts/README:5-16): wvl [nwvl] nm, tau5 [5][nwvl][20] in the
- * order H2O, CO2, O3, CH4, N2O (top-down layers), h2o_ref [20] = H2O VMR the H2O table holds. */
+/* Upload line-by-line tables (lbl.arts/README:5-16) and switch the solver to the LBL path:
+ * wvl [nwvl] nm ascending, tau5 [5][nwvl][20] in the order H2O, CO2, O3, CH4, N2O (top-down layers, as
+ * read by rcm_ascii_file2xy2D), h2o_ref / o3_ref [20] = layer VMRs the H2O / O3 tables were computed for
+ * (o3_ref NULL: O3 table used unscaled), co2_factor as `factor` in main.cpp:452-456.
+ * tau = tau_H2O*(H2O/h2o_ref) + co2_factor*tau_CO2 + tau_O3*(O3/o3_ref) + tau_CH4 + tau_N2O; the source is
+ * cplkavg() over bins bounded by the midpoints between adjacent wavelengths. */
 int rcm_set_lbl_tables(rcm_solver* s, const double* wvl, const double* tau5, int nwvl, const double* h2o_ref,
-                       double co2_factor);
+                       const double* o3_ref, double co2_factor);
+/* Synthetic LBL tables in the reference's format (the real lbl.*.asc are not distributed):
+ * wvl [nwvl] log-spaced 4-100 um, tau5 [5][nwvl][20]; deterministic in seed. */
+int rcm_make_lbl_tables(int nwvl, unsigned long long seed, const double* plevel_hPa, const double* h2o_vmr_layer,
+                        const double* o3_vmr_layer, double* wvl, double* tau5);
+/* Write one species table as text: "wavelength[nm] dtau(20 layers, top-down)" per line (lbl.arts/README:5-11). */
+int rcm_write_lbl_asc(const char* path, int nwvl, const double* wvl, const double* tau);
 
 /* Column state.  plevel_hPa [21] is shared by the ensemble.  Tlayer [ncol][20], Tsurf [ncol],
  * vmr9 [ncol][9][20], rel_hum [ncol][20].  Resets the step counter to 0 (the first step then

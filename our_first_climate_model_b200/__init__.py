@@ -7,9 +7,9 @@ ctypes binding used by the tests, the bench and Python drivers; it contains no n
 no CPU fallback - every compute call fails loudly when the library or a GPU is missing.
 """
 from .capi import (RcmError, Solver, Table, StepScalars, default_params, default_solar_params, solar_setup,  # noqa: F401
-                   lowerpos, read_atm, init_columns, make_ensemble, ascii_file2xy2D, cplkavg_host, device_count,
+                   lowerpos, read_atm, init_columns, make_ensemble, make_lbl_tables, write_lbl_asc, ascii_file2xy2D, cplkavg_host, device_count,
                    library_path, load_library, build_library, DECLARED_SYMBOLS)
 
 __all__ = ["RcmError", "Solver", "Table", "StepScalars", "default_params", "default_solar_params", "solar_setup",
-           "lowerpos", "read_atm", "init_columns", "make_ensemble", "ascii_file2xy2D", "cplkavg_host", "device_count",
+           "lowerpos", "read_atm", "init_columns", "make_ensemble", "make_lbl_tables", "write_lbl_asc", "ascii_file2xy2D", "cplkavg_host", "device_count",
            "library_path", "load_library", "build_library", "DECLARED_SYMBOLS"]

@@ -219,6 +219,21 @@ def make_ensemble(ncol, seed, plevel, base_Tlevel, base_vmr_ppm_level):
     return T, v
 
 
+def make_lbl_tables(nwvl, seed, plevel, h2o_vmr_layer, o3_vmr_layer):
+    """Synthetic LBL tables: -> (wvl[nwvl] nm, tau5[5, nwvl, 20]) in the order H2O, CO2, O3, CH4, N2O."""
+    wvl = np.zeros(nwvl)
+    tau5 = np.zeros((5, nwvl, NLAY))
+    _check(load_library().rcm_make_lbl_tables(C.c_int(nwvl), C.c_ulonglong(seed), _p(_f64(plevel, (NLEV,))),
+                                              _p(_f64(h2o_vmr_layer, (NLAY,))), _p(_f64(o3_vmr_layer, (NLAY,))),
+                                              _p(wvl), _p(tau5)))
+    return wvl, tau5
+
+
+def write_lbl_asc(path, wvl, tau):
+    wvl = _f64(wvl)
+    _check(load_library().rcm_write_lbl_asc(path.encode(), C.c_int(wvl.size), _p(wvl), _p(_f64(tau, (wvl.size, NLAY)))))
+
+
 def ascii_file2xy2D(path: str):
     """-> (status, x[nx], y[nx, ny]) with the reference's status codes."""
     L = load_library()
@@ -296,11 +311,12 @@ class Solver:
         _check(_lib.rcm_set_repwvl_table_from(self._h, table._h), self._h)
         self.nwvl = table.n_wvl
 
-    def set_lbl_tables(self, wvl, tau5, h2o_ref, co2_factor=1.0):
+    def set_lbl_tables(self, wvl, tau5, h2o_ref, o3_ref=None, co2_factor=1.0):
         wvl = _f64(wvl)
         tau5 = _f64(tau5, (5, wvl.size, NLAY))
+        o3 = None if o3_ref is None else _f64(o3_ref, (NLAY,))
         _check(_lib.rcm_set_lbl_tables(self._h, _p(wvl), _p(tau5), C.c_int(wvl.size), _p(_f64(h2o_ref, (NLAY,))),
-                                       C.c_double(co2_factor)), self._h)
+                                       _p(o3), C.c_double(co2_factor)), self._h)
         self.nwvl = wvl.size
 
     # columns

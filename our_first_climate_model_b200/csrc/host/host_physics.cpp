@@ -4,6 +4,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <cstring>
 
 #include "rcm_internal.h"
@@ -263,3 +264,59 @@ double rcm_cplkavg_host(double wvllo, double wvlhi, double t, int* status) {
 }
 
 }  // extern "C"
+
+// ---- synthetic line-by-line tables (the reference's lbl.*.asc are not distributed) -------------
+// Smooth band envelopes (Gaussians in ln lambda at the main thermal bands of each gas) times a
+// lognormal "line" factor per wavelength, times the absorber amount of the layer.  Only meant to
+// have the right shape, dynamic range (1e-8 .. 1e3) and format; documented in DESIGN.md.
+extern "C" int rcm_make_lbl_tables(int nwvl, unsigned long long seed, const double* plevel, const double* h2o,
+                                   const double* o3, double* wvl, double* tau5) {
+    if (nwvl < 2 || !plevel || !h2o || !o3 || !wvl || !tau5) return RCM_ERR_ARG;
+    struct Band { double center_um, width, strength; };
+    static const Band bands[5][3] = {
+        {{6.3, 0.12, 300.0}, {40.0, 0.55, 1500.0}, {12.0, 0.6, 0.3}},   // H2O: nu2, rotation, continuum-like
+        {{15.0, 0.07, 300.0}, {4.3, 0.03, 3000.0}, {10.4, 0.03, 0.02}}, // CO2
+        {{9.6, 0.03, 3.0}, {14.2, 0.04, 0.3}, {4.75, 0.02, 0.2}},        // O3
+        {{7.7, 0.04, 1.0}, {0, 0, 0}, {0, 0, 0}},                        // CH4
+        {{7.8, 0.03, 0.6}, {4.5, 0.02, 3.0}, {17.0, 0.03, 0.1}}};        // N2O
+    const int NL = RCM_NLAYER;
+    const double lo = std::log(4000.0), hi = std::log(100000.0);
+    for (int i = 0; i < nwvl; ++i) wvl[i] = std::exp(lo + (hi - lo) * (double)i / (double)(nwvl - 1));
+    for (int sp = 0; sp < 5; ++sp) {
+        Rng g{seed * 0x9E3779B97F4A7C15ull + 77777ull * (sp + 1)};
+        for (int i = 0; i < nwvl; ++i) {
+            const double lx = std::log(wvl[i] / 1000.0);
+            double env = 0.0;
+            for (const Band& b : bands[sp])
+                if (b.width > 0) {
+                    const double z = (lx - std::log(b.center_um)) / b.width;
+                    env += b.strength * std::exp(-0.5 * z * z);
+                }
+            const double line = std::exp(1.5 * g.normal());
+            for (int l = 0; l < NL; ++l) {
+                const double dp = (plevel[l + 1] - plevel[l]) / 50.0;
+                const double pm = (plevel[l + 1] + plevel[l]) / 2000.0;
+                double amount = dp;
+                if (sp == 0) amount *= h2o[l] / 7.0e-3;
+                if (sp == 2) amount *= o3[l] / 1.0e-6;
+                // pressure broadening: weaker absorption aloft in the band wings
+                tau5[((size_t)sp * nwvl + i) * NL + l] = (env * line * (0.3 + 0.7 * pm) + 1e-8) * amount / NL;
+            }
+        }
+    }
+    return RCM_OK;
+}
+
+extern "C" int rcm_write_lbl_asc(const char* path, int nwvl, const double* wvl, const double* tau) {
+    if (!path || !wvl || !tau || nwvl < 1) return RCM_ERR_ARG;
+    FILE* f = std::fopen(path, "w");
+    if (!f) return RCM_ERR_IO;
+    std::fprintf(f, "# wavelength [nm], delta_tau for the 20 layers, sorted top-down (lbl.arts/README)\n");
+    for (int i = 0; i < nwvl; ++i) {
+        std::fprintf(f, "%.17g", wvl[i]);
+        for (int l = 0; l < RCM_NLAYER; ++l) std::fprintf(f, " %.17g", tau[(size_t)i * RCM_NLAYER + l]);
+        std::fprintf(f, "\n");
+    }
+    std::fclose(f);
+    return RCM_OK;
+}

@@ -43,6 +43,14 @@ struct rcm_solver {
     size_t diag_steps = 0, tau_cap = 0;
     long step_index = 0;
     bool tau_valid = false;
+    // line-by-line tables
+    bool lbl_mode = false;
+    int lbl_nwvl = 0;
+    double lbl_co2_factor = 1.0;
+    bool lbl_has_o3_ref = false;
+    double *d_lbl_lo = nullptr, *d_lbl_hi = nullptr, *d_lbl_tau5 = nullptr, *d_lbl_h2o_ref = nullptr,
+           *d_lbl_o3_ref = nullptr, *d_sH = nullptr, *d_sO = nullptr, *d_dTstat = nullptr, *d_part = nullptr;
+    size_t part_cap = 0;
     std::vector<double> stage;  // host packing buffer
     std::string err;
     long launches = 0;
@@ -217,6 +225,7 @@ int ensure_columns(rcm_solver* s, int ncol) {
     CU(dalloc(s->d_lowpos, n * NLAY));
     s->cap = ncol;
     s->diag_steps = 0;
+    s->part_cap = 0;
     return RCM_OK;
 }
 
@@ -351,7 +360,8 @@ int rcm_destroy(rcm_solver* s) {
     cudaSetDevice(s->device);
     cudaStreamSynchronize(s->stream);
     void* ptrs[] = {s->d_xsec_file, s->d_coef, s->d_species, s->d_planck_c, s->d_planck_k, s->d_exp_tab, s->d_T, s->d_Ts, s->d_vmr, s->d_rh,
-                    s->d_Tprev, s->d_time, s->d_Ed, s->d_Eu, s->d_dE, s->d_dt, s->d_diag, s->d_scalars, s->d_tau,
+                    s->d_Tprev, s->d_time, s->d_lbl_lo, s->d_lbl_hi, s->d_lbl_tau5, s->d_lbl_h2o_ref, s->d_lbl_o3_ref, s->d_sH, s->d_sO,
+                    s->d_dTstat, s->d_part, s->d_Ed, s->d_Eu, s->d_dE, s->d_dt, s->d_diag, s->d_scalars, s->d_tau,
                     s->d_lowpos};
     for (void* q : ptrs)
         if (q) cudaFree(q);
@@ -444,6 +454,7 @@ int rcm_set_repwvl_table(rcm_solver* s, const double* xsec, const double* wvl, c
     s->dc.n_p = n_p;
     for (int m = 0; m < n_tpert; ++m) s->dc.t_pert[m] = t_pert[m];
     s->has_table = true;
+    s->lbl_mode = false;
     s->const_dirty = true;
     s->tau_valid = false;
     s->tau_cap = 0;
@@ -456,8 +467,40 @@ int rcm_set_repwvl_table_from(rcm_solver* s, const rcm_table* t) {
                                 t->t_pert.data(), t->n_tpert, t->n_species, t->n_wvl, t->n_p);
 }
 
-int rcm_set_lbl_tables(rcm_solver* s, const double*, const double*, int, const double*, double) {
-    return fail(s, RCM_ERR_STATE, "line-by-line tables: not available in this build");
+int rcm_set_lbl_tables(rcm_solver* s, const double* wvl, const double* tau5, int nwvl, const double* h2o_ref,
+                       const double* o3_ref, double co2_factor) {
+    if (!s || !wvl || !tau5 || nwvl < 2 || !h2o_ref) return RCM_ERR_ARG;
+    for (int i = 1; i < nwvl; ++i)
+        if (!(wvl[i] > wvl[i - 1])) return fail(s, RCM_ERR_ARG, "LBL wavelengths must be strictly ascending");
+    CU(cudaSetDevice(s->device));
+    // spectral bins: bounded by the midpoints between adjacent wavelengths, end bins mirrored
+    // (builder decision; cplkavg() needs hi > lo, cplkavg.cpp:144-146)
+    std::vector<double> lo(nwvl), hi(nwvl);
+    for (int i = 0; i < nwvl; ++i) {
+        const double dl = (i > 0) ? (wvl[i] - wvl[i - 1]) : (wvl[1] - wvl[0]);
+        const double dh = (i < nwvl - 1) ? (wvl[i + 1] - wvl[i]) : (wvl[i] - wvl[i - 1]);
+        lo[i] = wvl[i] - dl / 2.0;
+        hi[i] = wvl[i] + dh / 2.0;
+    }
+    const size_t n = (size_t)nwvl;
+    CU(dalloc(s->d_lbl_lo, n));
+    CU(dalloc(s->d_lbl_hi, n));
+    CU(dalloc(s->d_lbl_tau5, 5 * n * NLAY));
+    CU(dalloc(s->d_lbl_h2o_ref, (size_t)NLAY));
+    CU(dalloc(s->d_lbl_o3_ref, (size_t)NLAY));
+    CU(cudaMemcpy(s->d_lbl_lo, lo.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(s->d_lbl_hi, hi.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(s->d_lbl_tau5, tau5, 5 * n * NLAY * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(s->d_lbl_h2o_ref, h2o_ref, NLAY * sizeof(double), cudaMemcpyHostToDevice));
+    s->lbl_has_o3_ref = o3_ref != nullptr;
+    if (o3_ref) CU(cudaMemcpy(s->d_lbl_o3_ref, o3_ref, NLAY * sizeof(double), cudaMemcpyHostToDevice));
+    s->lbl_nwvl = nwvl;
+    s->lbl_co2_factor = co2_factor;
+    s->lbl_mode = true;
+    s->dc.nwvl = nwvl;
+    s->const_dirty = true;
+    s->part_cap = 0;
+    return RCM_OK;
 }
 
 int rcm_set_columns(rcm_solver* s, int ncol, const double* plevel_hPa, const double* Tlayer, const double* Tsurf,
@@ -551,12 +594,70 @@ int rcm_radiative_transfer(rcm_solver* s, const double* tau, double* E_down, dou
     return RCM_OK;
 }
 
+static int lbl_advance(rcm_solver* s, int nsteps) {
+    if (s->h2o_slot < 0) return fail(s, RCM_ERR_STATE, "the LBL path needs H2O in species_mask");
+    int st = refresh_const(s);
+    if (st != RCM_OK) return st;
+    const size_t n = (size_t)s->ncol;
+    if (!s->d_sH || s->part_cap == 0) {
+        CU(dalloc(s->d_sH, (size_t)s->cap * NLAY));
+        CU(dalloc(s->d_sO, (size_t)s->cap * NLAY));
+        CU(dalloc(s->d_dTstat, (size_t)s->cap));
+    }
+    LblArgs a{};
+    a.ncol = s->ncol;
+    a.ntiles = (s->ncol + 31) / 32;
+    a.nwvl = s->lbl_nwvl;
+    // enough (tile, wavelength chunk) CTAs to fill the GPU a few times over; chunk length a multiple of 3 groups
+    int nchunks = (4 * 296 + a.ntiles - 1) / a.ntiles;
+    if (nchunks > a.nwvl / 48) nchunks = a.nwvl / 48;
+    if (nchunks < 1) nchunks = 1;
+    a.chunk_len = ((a.nwvl + nchunks - 1) / nchunks + 2) / 3 * 3;
+    a.nchunks = (a.nwvl + a.chunk_len - 1) / a.chunk_len;
+    const size_t need = (size_t)a.nchunks * n * 42;
+    if (need > s->part_cap) {
+        CU(dalloc(s->d_part, need));
+        s->part_cap = need;
+    }
+    a.nact = s->nactive;
+    a.h2o_slot = s->h2o_slot;
+    a.o3_slot = -1;
+    for (int k = 0; k < s->nactive; ++k)
+        if (s->species[k] == 2) a.o3_slot = k;
+    a.co2_factor = s->lbl_co2_factor;
+    a.wvl_lo = s->d_lbl_lo;
+    a.wvl_hi = s->d_lbl_hi;
+    a.tau5 = s->d_lbl_tau5;
+    a.h2o_ref = s->d_lbl_h2o_ref;
+    a.o3_ref = s->lbl_has_o3_ref ? s->d_lbl_o3_ref : nullptr;
+    a.exp_tab = s->d_exp_tab;
+    a.Tlayer = s->d_T; a.Tsurf = s->d_Ts; a.vmr = s->d_vmr; a.rel_hum = s->d_rh; a.Tprev = s->d_Tprev;
+    a.time_h = s->d_time; a.sH = s->d_sH; a.sO = s->d_sO; a.dTstat = s->d_dTstat; a.part = s->d_part;
+    a.E_down = s->d_Ed; a.E_up = s->d_Eu; a.dE = s->d_dE; a.dt = s->d_dt;
+    for (int k = 0; k < nsteps; ++k) {
+        a.step_index = s->step_index + k;
+        a.diag = s->d_diag + (size_t)k * s->ncol * 4;
+        CU(rcm_launch_lbl_step(a, s->stream));
+        s->launches += 3;
+    }
+    return RCM_OK;
+}
+
 int rcm_advance_async(rcm_solver* s, int nsteps, double** d_scalars) {
     if (!s || nsteps <= 0) return RCM_ERR_ARG;
-    if (!s->has_table || s->ncol <= 0) return fail(s, RCM_ERR_STATE, "table and columns must be loaded");
+    if ((!s->has_table && !s->lbl_mode) || s->ncol <= 0) return fail(s, RCM_ERR_STATE, "table and columns must be loaded");
     CU(cudaSetDevice(s->device));
     int st = ensure_diag(s, nsteps);
     if (st != RCM_OK) return st;
+    if (s->lbl_mode) {
+        st = lbl_advance(s, nsteps);
+        if (st != RCM_OK) return st;
+        CU(rcm_launch_reduce_diag(s->d_diag, nsteps, s->ncol, s->p.dT_converged, s->d_scalars, s->stream));
+        s->launches += 1;
+        s->step_index += nsteps;
+        if (d_scalars) *d_scalars = s->d_scalars;
+        return RCM_OK;
+    }
     st = launch(s, MODE_STEP, nsteps, true);
     if (st != RCM_OK) return st;
     CU(rcm_launch_reduce_diag(s->d_diag, nsteps, s->ncol, s->p.dT_converged, s->d_scalars, s->stream));

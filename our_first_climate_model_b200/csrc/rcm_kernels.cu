@@ -95,6 +95,93 @@ __device__ __forceinline__ int lowerpos_t(double tref, double x, int n) {
     return res;
 }
 
+// ------------------------------------------------------------------------------------------
+// K3 + K4 for one (column, wavelength, half): from the optical depths tau[j] and the Planck source
+// Bo[j] of the ten owned layers (Bs: surface source) accumulate the fluxes over all angles.
+// Written for the deviation of the radiance from the source of the NEXT layer,
+//   down: N_{lev+1} = L_{lev+1} - B_{lev+1} = t_lev N_lev + (B_lev - B_{lev+1}),    N_0  = -B_0
+//   up:   V_lev     = U_lev - B_{lev-1}     = t_lev V_{lev+1} + (B_lev - B_{lev-1}), V_20 = B_s - B_19
+// which is the reference's L = (1-alpha) L + alpha B, alpha = 1 - t (main.cpp:307/312), at one FMA per
+// layer and sweep; the angle-independent parts sum_mu cmu*B (and main.cpp:302) are added up front.
+// Lane h=0 runs the down sweep through its layers 0..9 while lane h=1 runs the up sweep through 19..10;
+// they swap the radiance at level 10 and each finishes the other's sweep through its own layers.  Both
+// lanes execute identical code.  Two angles (streams A and B of the schedule) are carried at once:
+// their dependency chains are independent, which doubles the instruction-level parallelism.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sweep_item(const double (&tau)[HALF], const double (&Bo)[HALF], double Bs, int h,
+                                           const double* __restrict__ tab_lane, double (&E1)[HALF],
+                                           double (&E2)[HALF], double& Eu20) {
+    double D1[HALF], Dx, X0;
+    {
+        const double Bnb = __shfl_xor_sync(0xffffffffu, Bo[HALF - 1], 1);  // partner's boundary layer
+        const double cs = cst.csum;
+#pragma unroll
+        for (int j = 0; j < HALF; ++j) {
+            const double Bnext = (j < HALF - 1) ? Bo[j + 1] : Bnb;
+            D1[j] = Bo[j] - Bnext;
+            E1[j] = fma(cs, Bnext, E1[j]);
+            if (j > 0) E2[j] = fma(cs, Bo[j - 1], E2[j]);
+        }
+        Dx = Bo[0];
+        const double Bstart = h ? Bs : 0.0;  // down sweep starts with L=0, up sweep with B(T_surface)
+        X0 = Bstart - Bo[0];
+        Eu20 = fma(cs, Bstart, Eu20);  // main.cpp:302 summed over the angles (h=1 only)
+    }
+    const int nslot = cst.nslot;
+    double tA[HALF], tB[HALF];
+    for (int is = 0; is < nslot; ++is) {
+        const double cmA = cst.cmu[0][is], cmB = cst.cmu[1][is];
+        const int kind = cst.cube[0][is] | (cst.cube[1][is] << 1);
+        const double nimA = cst.neg_inv_mu_l2e[0][is], nimB = cst.neg_inv_mu_l2e[1][is];
+        if (kind == 0) {
+#pragma unroll
+            for (int j = 0; j < HALF; ++j) {
+                tA[j] = exp_scaled(tau[j], nimA, tab_lane);
+                tB[j] = exp_scaled(tau[j], nimB, tab_lane);
+            }
+        } else if (kind == 1) {  // 1/mu of slot A is three times its previous slot's: t <- t^3
+#pragma unroll
+            for (int j = 0; j < HALF; ++j) {
+                tA[j] = tA[j] * tA[j] * tA[j];
+                tB[j] = exp_scaled(tau[j], nimB, tab_lane);
+            }
+        } else if (kind == 2) {
+#pragma unroll
+            for (int j = 0; j < HALF; ++j) {
+                tA[j] = exp_scaled(tau[j], nimA, tab_lane);
+                tB[j] = tB[j] * tB[j] * tB[j];
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < HALF; ++j) {
+                tA[j] = tA[j] * tA[j] * tA[j];
+                tB[j] = tB[j] * tB[j] * tB[j];
+            }
+        }
+        double XA = X0, XB = X0;
+#pragma unroll
+        for (int j = 0; j < HALF; ++j) {
+            XA = fma(tA[j], XA, D1[j]);
+            XB = fma(tB[j], XB, D1[j]);
+            E1[j] = fma(cmA, XA, E1[j]);
+            E1[j] = fma(cmB, XB, E1[j]);
+        }
+        double YA = __shfl_xor_sync(0xffffffffu, XA, 1);
+        double YB = __shfl_xor_sync(0xffffffffu, XB, 1);
+#pragma unroll
+        for (int j = HALF - 1; j >= 1; --j) {
+            YA = fma(tA[j], YA, -D1[j - 1]);
+            YB = fma(tB[j], YB, -D1[j - 1]);
+            E2[j] = fma(cmA, YA, E2[j]);
+            E2[j] = fma(cmB, YB, E2[j]);
+        }
+        YA = fma(tA[0], YA, Dx);
+        YB = fma(tB[0], YB, Dx);
+        E2[0] = fma(cmA, YA, E2[0]);
+        E2[0] = fma(cmB, YB, E2[0]);
+    }
+}
+
 // Layer split.  The two lanes of a pair share one (column, wavelength): lane h=0 owns layers 0..9
 // top-down, lane h=1 owns layers 19..10 (bottom-up), both as local index j=0..9.  Per-layer
 // arrays are stored in this order: row(l) = l for l<10, 29-l otherwise (= 10*h + j).
@@ -160,7 +247,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 || NT == 512) ? 512 / NT : 384 
 
     for (int i = tid; i < EXP_TAB * 32; i += NT) s.exp_tab[i] = a.exp_tab[i >> 5];
     const double* tab_lane = s.exp_tab + lane;
-    const int nslot = cst.nslot, nwvl = cst.nwvl;
+    const int nwvl = cst.nwvl;
 
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
         const int col0 = tile * C;
@@ -308,90 +395,12 @@ __global__ void __launch_bounds__(NT, (NT == 256 || NT == 512) ? 512 / NT : 384 
                 // K2: Planck source B_l = k_w / (exp(c_w / T_l) - 1) (main.cpp:188-191 regrouped so that
                 // everything that depends on the wavelength alone is precomputed on the host).
                 const double pc = __ldg(a.planck_c + w), pk = __ldg(a.planck_k + w);
-                double D1[HALF], Dx, X0;
-                {
-                    double Bo[HALF];
+                double Bo[HALF];
 #pragma unroll
-                    for (int j = 0; j < HALF; ++j)
-                        Bo[j] = div_fast(pk, exp_scaled(pc, s.invT[sb + j * C] * L2E64, tab_lane) - 1.0);
-                    const double Bnb = __shfl_xor_sync(0xffffffffu, Bo[HALF - 1], 1);  // partner's boundary layer
-                    const double Bs = div_fast(pk, exp_scaled(pc, s.invTs[c] * L2E64, tab_lane) - 1.0);  // main.cpp:301
-                    const double cs = cst.csum;
-                    // angle-independent parts of the fluxes: sum_mu cmu * B (see the recurrences below)
-#pragma unroll
-                    for (int j = 0; j < HALF; ++j) {
-                        const double Bnext = (j < HALF - 1) ? Bo[j + 1] : Bnb;
-                        D1[j] = Bo[j] - Bnext;
-                        E1[j] = fma(cs, Bnext, E1[j]);
-                        if (j > 0) E2[j] = fma(cs, Bo[j - 1], E2[j]);
-                    }
-                    Dx = Bo[0];
-                    const double Bstart = h ? Bs : 0.0;  // down sweep starts with L=0, up sweep with B(T_surface)
-                    X0 = Bstart - Bo[0];
-                    Eu20 = fma(cs, Bstart, Eu20);  // main.cpp:302 summed over the angles (h=1 only)
-                }
-
-                // K3 + K4.  Written for the deviation of the radiance from the source of the NEXT layer,
-                //   down: N_{lev+1} = L_{lev+1} - B_{lev+1} = t_lev N_lev + (B_lev - B_{lev+1}),    N_0  = -B_0
-                //   up:   V_lev     = U_lev - B_{lev-1}     = t_lev V_{lev+1} + (B_lev - B_{lev-1}), V_20 = B_s - B_19
-                // which is the reference's L = (1-alpha) L + alpha B, alpha = 1 - t (main.cpp:307/312), at one
-                // FMA per layer and sweep.  Lane h=0 runs the down sweep through its layers 0..9 while lane h=1
-                // runs the up sweep through 19..10; they swap the radiance at level 10 and each finishes the
-                // other's sweep through its own layers.  Both lanes execute identical code.
-                // Two angles are carried at once (streams A and B of the schedule): their dependency chains are
-                // independent, which doubles the instruction-level parallelism of the sweeps.
-                double tA[HALF], tB[HALF];
-                for (int is = 0; is < nslot; ++is) {
-                    const double cmA = cst.cmu[0][is], cmB = cst.cmu[1][is];
-                    const int kind = cst.cube[0][is] | (cst.cube[1][is] << 1);
-                    const double nimA = cst.neg_inv_mu_l2e[0][is], nimB = cst.neg_inv_mu_l2e[1][is];
-                    if (kind == 0) {
-#pragma unroll
-                        for (int j = 0; j < HALF; ++j) {
-                            tA[j] = exp_scaled(tau[j], nimA, tab_lane);
-                            tB[j] = exp_scaled(tau[j], nimB, tab_lane);
-                        }
-                    } else if (kind == 1) {  // 1/mu of slot A is three times its previous slot's: t <- t^3
-#pragma unroll
-                        for (int j = 0; j < HALF; ++j) {
-                            tA[j] = tA[j] * tA[j] * tA[j];
-                            tB[j] = exp_scaled(tau[j], nimB, tab_lane);
-                        }
-                    } else if (kind == 2) {
-#pragma unroll
-                        for (int j = 0; j < HALF; ++j) {
-                            tA[j] = exp_scaled(tau[j], nimA, tab_lane);
-                            tB[j] = tB[j] * tB[j] * tB[j];
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < HALF; ++j) {
-                            tA[j] = tA[j] * tA[j] * tA[j];
-                            tB[j] = tB[j] * tB[j] * tB[j];
-                        }
-                    }
-                    double XA = X0, XB = X0;
-#pragma unroll
-                    for (int j = 0; j < HALF; ++j) {
-                        XA = fma(tA[j], XA, D1[j]);
-                        XB = fma(tB[j], XB, D1[j]);
-                        E1[j] = fma(cmA, XA, E1[j]);
-                        E1[j] = fma(cmB, XB, E1[j]);
-                    }
-                    double YA = __shfl_xor_sync(0xffffffffu, XA, 1);
-                    double YB = __shfl_xor_sync(0xffffffffu, XB, 1);
-#pragma unroll
-                    for (int j = HALF - 1; j >= 1; --j) {
-                        YA = fma(tA[j], YA, -D1[j - 1]);
-                        YB = fma(tB[j], YB, -D1[j - 1]);
-                        E2[j] = fma(cmA, YA, E2[j]);
-                        E2[j] = fma(cmB, YB, E2[j]);
-                    }
-                    YA = fma(tA[0], YA, Dx);
-                    YB = fma(tB[0], YB, Dx);
-                    E2[0] = fma(cmA, YA, E2[0]);
-                    E2[0] = fma(cmB, YB, E2[0]);
-                }
+                for (int j = 0; j < HALF; ++j)
+                    Bo[j] = div_fast(pk, exp_scaled(pc, s.invT[sb + j * C] * L2E64, tab_lane) - 1.0);
+                const double Bs = div_fast(pk, exp_scaled(pc, s.invTs[c] * L2E64, tab_lane) - 1.0);  // main.cpp:301
+                sweep_item(tau, Bo, Bs, h, tab_lane, E1, E2, Eu20);
             }
             if (MODE == MODE_TAU) continue;
 
@@ -595,7 +604,7 @@ __global__ void __launch_bounds__(256) rcm_microbench_kernel(double* out, long i
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ double plkf(double x) { return x * x * x / (exp(x) - 1.); }
 
-__device__ double cplkavg_dev(double wvllo, double wvlhi, double t) {
+__device__ __noinline__ double cplkavg_dev(double wvllo, double wvlhi, double t) {
     const double c2 = 1.438786, sigma = 5.67032E-8, vcut = 1.5;
     const double a1 = 1. / 3., a2 = -1. / 8., a3 = 1. / 60., a4 = -1. / 5040., a5 = 1. / 272160.,
                  a6 = -1. / 13305600.;
@@ -643,6 +652,174 @@ __device__ double cplkavg_dev(double wvllo, double wvlhi, double t) {
     }
     const double ans = (smallv == 2) ? p[1] - p[0] : (smallv == 1) ? 1. - p[0] - d[1] : d[0] - d[1];
     return ans * (sigdpi * t4);
+}
+
+// ------------------------------------------------------------------------------------------
+// Line-by-line path (BASELINE configs 3 and 5).  The reference ships the table format
+// (lbl.arts/README:5-16), the reader and cplkavg() but no driver; the composition below is the one
+// documented in DESIGN.md section 5 (and restated on the CPU for the tests):
+//   tau = tau_H2O*s_H2O(l) + f_CO2*tau_CO2 + tau_O3*s_O3(l) + tau_CH4 + tau_N2O   (left to right)
+//   source = cplkavg(lo_w, hi_w, T) with unit spectral weight, sweeps as main.cpp:297-341.
+// Three kernels per step: prep (theta-sort, feedback, scale factors), rt (tau, source, sweeps,
+// partial fluxes per wavelength chunk), finish (sum of the chunks, dE, time step, T update).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) rcm_lbl_prep_kernel(const LblArgs a) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= a.ncol) return;
+    double th[NLAY];
+#pragma unroll
+    for (int l = 0; l < NLAY; ++l) th[l] = a.Tlayer[(size_t)col * NLAY + l] * cst.conv[l];  // main.cpp:536
+#pragma unroll
+    for (int pass = 0; pass < NLAY; ++pass) {
+#pragma unroll
+        for (int l = (pass & 1); l + 1 < NLAY; l += 2) cex(th[l], th[l + 1]);
+    }
+    double dmax = 0.0;
+#pragma unroll
+    for (int l = 0; l < NLAY; ++l) {
+        const size_t gi = (size_t)col * NLAY + l;
+        const double Tn = th[l] / cst.conv[l];  // main.cpp:540
+        a.Tlayer[gi] = Tn;
+        dmax = fmax(dmax, fabs(Tn - a.Tprev[gi]));
+        a.Tprev[gi] = Tn;
+        double h2o = a.vmr[((size_t)col * a.nact + a.h2o_slot) * NLAY + l];
+        if (a.step_index != 0) {  // water_vapor_feedback, main.cpp:281-289
+            const double Tc = Tn - 273.15;
+            h2o = a.rel_hum[gi] * (6.1094 * exp(17.625 * Tc / (Tc + 243.04))) / cst.player[l];
+            a.vmr[((size_t)col * a.nact + a.h2o_slot) * NLAY + l] = h2o;
+        }
+        a.sH[gi] = h2o / a.h2o_ref[l];
+        a.sO[gi] = (a.o3_slot >= 0 && a.o3_ref) ? a.vmr[((size_t)col * a.nact + a.o3_slot) * NLAY + l] / a.o3_ref[l] : 1.0;
+    }
+    a.dTstat[col] = dmax;
+}
+
+template <int C, int NT>
+__global__ void __launch_bounds__(NT, 384 / NT) rcm_lbl_rt_kernel(const LblArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int G = NT / (2 * C), GC = G * C;
+    double* p = reinterpret_cast<double*>(smem_raw);
+    double* s_tab = p; p += EXP_TAB * 32;
+    double* s_T = p;   p += NLAY * C;
+    double* s_sH = p;  p += NLAY * C;
+    double* s_sO = p;  p += NLAY * C;
+    double* s_Ts = p;  p += C;
+    double* s_Ep = p;  // [21][GC]
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int h = tid & 1, q = tid >> 1, c = q % C, g = q / C;
+    const int sb = h * HALF * C + c;
+    for (int i = tid; i < EXP_TAB * 32; i += NT) s_tab[i] = a.exp_tab[i >> 5];
+    const double* tab_lane = s_tab + lane;
+    const int tile = blockIdx.x % a.ntiles, chunk = blockIdx.x / a.ntiles;
+    const int col0 = tile * C, ncl = min(C, a.ncol - col0);
+    for (int i = tid; i < NLAY * C; i += NT) {
+        const int l = i / C, cc = i % C, r = prow(l) * C + cc;
+        const bool ok = cc < ncl;
+        const size_t gi = (size_t)(col0 + cc) * NLAY + l;
+        s_T[r] = ok ? a.Tlayer[gi] : 250.0;
+        s_sH[r] = ok ? a.sH[gi] : 1.0;
+        s_sO[r] = ok ? a.sO[gi] : 1.0;
+    }
+    if (tid < C) s_Ts[tid] = (tid < ncl) ? a.Tsurf[col0 + tid] : 250.0;
+    __syncthreads();
+
+    double E1[HALF], E2[HALF], Eu20 = 0.0;
+#pragma unroll
+    for (int j = 0; j < HALF; ++j) E1[j] = E2[j] = 0.0;
+    const int w_lo = chunk * a.chunk_len, w_hi = min(a.nwvl, w_lo + a.chunk_len);
+    const size_t plane = (size_t)a.nwvl * NLAY;
+    for (int w = w_lo + g; w < w_hi; w += G) {
+        double tau[HALF], Bo[HALF];
+        const double lo = __ldg(a.wvl_lo + w), hi = __ldg(a.wvl_hi + w);
+        const double* t5 = a.tau5 + (size_t)w * NLAY;
+#pragma unroll
+        for (int j = 0; j < HALF; ++j) {
+            const int l = h ? (NLAY - 1 - j) : j;
+            double v = __dmul_rn(__ldg(t5 + l), s_sH[sb + j * C]);
+            v = __dadd_rn(v, __dmul_rn(a.co2_factor, __ldg(t5 + plane + l)));
+            v = __dadd_rn(v, __dmul_rn(__ldg(t5 + 2 * plane + l), s_sO[sb + j * C]));
+            v = __dadd_rn(v, __ldg(t5 + 3 * plane + l));
+            v = __dadd_rn(v, __ldg(t5 + 4 * plane + l));
+            if (cst.cloud_row == h * HALF + j) v = __dadd_rn(v, cst.cloud_tau);
+            tau[j] = v;
+            Bo[j] = cplkavg_dev(lo, hi, s_T[sb + j * C]);
+        }
+        const double Bs = cplkavg_dev(lo, hi, s_Ts[c]);
+        sweep_item(tau, Bo, Bs, h, tab_lane, E1, E2, Eu20);
+    }
+    // partial fluxes of this wavelength chunk: part[chunk][col][0..20] = E_down, [21..41] = E_up
+    double* part = a.part + ((size_t)chunk * a.ncol + col0) * 42;
+#pragma unroll
+    for (int j = 0; j < HALF; ++j) s_Ep[(h ? (NLAY - 1 - j) : j) * GC + g * C + c] = h ? E2[j] : E1[j];
+    __syncthreads();
+    for (int i = tid; i < NLAY * C; i += NT) {
+        const int l = i / C, cc = i % C;
+        double sum = 0.0;
+        for (int gg = 0; gg < G; ++gg) sum += s_Ep[l * GC + gg * C + cc];
+        if (cc < ncl) part[(size_t)cc * 42 + l + 1] = sum;
+    }
+    if (tid < ncl) part[(size_t)tid * 42] = 0.0;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < HALF; ++j) s_Ep[(h ? (NLAY - 1 - j) : j) * GC + g * C + c] = h ? E1[j] : E2[j];
+    if (h) s_Ep[NLAY * GC + g * C + c] = Eu20;
+    __syncthreads();
+    for (int i = tid; i < NLEV * C; i += NT) {
+        const int l = i / C, cc = i % C;
+        double sum = 0.0;
+        for (int gg = 0; gg < G; ++gg) sum += s_Ep[l * GC + gg * C + cc];
+        if (cc < ncl) part[(size_t)cc * 42 + 21 + l] = sum;
+    }
+}
+
+__global__ void __launch_bounds__(128) rcm_lbl_finish_kernel(const LblArgs a) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= a.ncol) return;
+    double Ed[NLEV], Eu[NLEV];
+#pragma unroll
+    for (int l = 0; l < NLEV; ++l) Ed[l] = Eu[l] = 0.0;
+    for (int k = 0; k < a.nchunks; ++k) {  // fixed order: deterministic
+        const double* pp = a.part + ((size_t)k * a.ncol + col) * 42;
+#pragma unroll
+        for (int l = 0; l < NLEV; ++l) {
+            Ed[l] += pp[l];
+            Eu[l] += pp[21 + l];
+        }
+    }
+    double dE[NLAY], mx = -1e300, mabs = 0.0;
+#pragma unroll
+    for (int l = 0; l < NLAY; ++l) {
+        double d = Ed[l] - Ed[l + 1] + Eu[l + 1] - Eu[l];                      // main.cpp:338
+        if (l == NLAY - 1) d += cst.solar_irr + Ed[NLAY] - Eu[NLAY];           // main.cpp:341
+        dE[l] = d;
+        if (mx < d) mx = d;
+        mabs = fmax(mabs, fabs(d));
+    }
+    double dt = (double)(float)cst.max_dT / mx * (1004.0 * cst.dp * 100.0) / 9.80665;  // main.cpp:157
+    if (dt > cst.dt_cap) dt = cst.dt_cap;
+    double Tl = 0.0;
+#pragma unroll
+    for (int l = 0; l < NLAY; ++l) {
+        const size_t gi = (size_t)col * NLAY + l;
+        Tl = a.Tlayer[gi] + dE[l] * dt * 9.80665 / (1004.0 * cst.dp * 100.0);  // main.cpp:169
+        a.Tlayer[gi] = Tl;
+        a.dE[gi] = dE[l];
+    }
+    a.Tsurf[col] = Tl * cst.conv[NLAY - 1];  // main.cpp:173
+    a.dt[col] = dt;
+    a.time_h[col] += (float)dt / 3600;
+#pragma unroll
+    for (int l = 0; l < NLEV; ++l) {
+        a.E_down[(size_t)col * NLEV + l] = Ed[l];
+        a.E_up[(size_t)col * NLEV + l] = Eu[l];
+    }
+    if (a.diag) {
+        double* dg = a.diag + (size_t)col * 4;
+        dg[0] = cst.solar_irr - Eu[0];
+        dg[1] = a.dTstat[col];
+        dg[2] = mabs;
+        dg[3] = dt;
+    }
 }
 
 __global__ void rcm_cplkavg_kernel(int n, const double* lo, const double* hi, const double* t, double* out) {
@@ -724,5 +901,21 @@ cudaError_t rcm_launch_microbench(int which, double* out, const double* tab, lon
 cudaError_t rcm_launch_cplkavg(int n, const double* lo, const double* hi, const double* t, double* out,
                                cudaStream_t st) {
     rcm_cplkavg_kernel<<<148, 256, 0, st>>>(n, lo, hi, t, out);
+    return cudaGetLastError();
+}
+
+size_t rcm_lbl_smem_bytes(int C, int nthreads) {
+    return ((size_t)EXP_TAB * 32 + (size_t)NLAY * C * 3 + C + (size_t)NLEV * (nthreads / 2)) * sizeof(double);
+}
+
+cudaError_t rcm_launch_lbl_step(const LblArgs& a, cudaStream_t st) {
+    constexpr int C = 32, NT = 192;
+    rcm_lbl_prep_kernel<<<(a.ncol + 127) / 128, 128, 0, st>>>(a);
+    const size_t smem = rcm_lbl_smem_bytes(C, NT);
+    auto kern = rcm_lbl_rt_kernel<C, NT>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<a.ntiles * a.nchunks, NT, smem, st>>>(a);
+    rcm_lbl_finish_kernel<<<(a.ncol + 127) / 128, 128, 0, st>>>(a);
     return cudaGetLastError();
 }

@@ -73,6 +73,23 @@ struct StepArgs {
     int h2o_slot;          // position of H2O in the active list, -1 if absent
 };
 
+// Line-by-line path: arguments of the three per-step kernels.
+struct LblArgs {
+    int ncol, ntiles, nwvl, nchunks, chunk_len, nact, h2o_slot, o3_slot;
+    long step_index;
+    double co2_factor;
+    const double* __restrict__ wvl_lo;   // [nwvl] bin edges, nm
+    const double* __restrict__ wvl_hi;
+    const double* __restrict__ tau5;     // [5][nwvl][20]  H2O, CO2, O3, CH4, N2O
+    const double* __restrict__ h2o_ref;  // [20]
+    const double* __restrict__ o3_ref;   // [20] or NULL
+    const double* __restrict__ exp_tab;
+    double* Tlayer; double* Tsurf; double* vmr; const double* rel_hum; double* Tprev; float* time_h;
+    double* sH; double* sO; double* dTstat;  // [ncol][20], [ncol][20], [ncol]
+    double* part;                            // [nchunks][ncol][42]
+    double* E_down; double* E_up; double* dE; double* dt; double* diag;
+};
+
 enum { MODE_STEP = 0, MODE_TAU = 1, MODE_RT = 2 };
 
 size_t rcm_step_smem_bytes(int C, int nactive, int nthreads);
@@ -84,6 +101,8 @@ cudaError_t rcm_launch_coef(const double* xsec_file, double* coef, int nt, int n
                             const int* d_species, cudaStream_t st);
 cudaError_t rcm_launch_microbench(int which, double* out, const double* tab, long iters, int grid,
                                   cudaStream_t st);
+size_t rcm_lbl_smem_bytes(int C, int nthreads);
+cudaError_t rcm_launch_lbl_step(const LblArgs& a, cudaStream_t st);
 cudaError_t rcm_launch_cplkavg(int n, const double* lo, const double* hi, const double* t, double* out,
                                cudaStream_t st);
 
