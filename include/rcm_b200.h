@@ -135,6 +135,9 @@ int rcm_set_repwvl_table(rcm_solver* s, const double* xsec, const double* wvl, c
                          const double* p_grid, const double* t_ref, const double* t_pert, int n_tpert,
                          int n_species, int n_wvl, int n_p);
 int rcm_set_repwvl_table_from(rcm_solver* s, const rcm_table* t);
+/* Wavelengths [nm] and spectral weights alone (what radiative_transfer, main.cpp:320-344, is handed):
+ * enough for rcm_radiative_transfer with a caller-supplied tau. */
+int rcm_set_spectral_grid(rcm_solver* s, const double* wvl, const double* weight, int n_wvl);
 
 /* Upload line-by-line tables (lbl.arts/README:5-16) and switch the solver to the LBL path:
  * wvl [nwvl] nm ascending, tau5 [5][nwvl][20] in the order H2O, CO2, O3, CH4, N2O (top-down layers, as

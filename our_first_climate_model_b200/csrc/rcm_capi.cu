@@ -25,7 +25,7 @@ struct rcm_solver {
     int opt_config = 3;        // 0: 512 threads x 64 columns, 1: 256 threads x 32 columns (2 CTAs/SM), 2: 384x64, 3: 192x32
     int opt_stagger = 0;       // de-phasing delay in cycles (0 = off)
     // table
-    bool has_table = false;
+    bool has_table = false, has_spectral = false;
     std::vector<double> p_grid, t_ref, t_pert, wvl, weight;
     double *d_xsec_file = nullptr, *d_coef = nullptr, *d_planck_c = nullptr, *d_planck_k = nullptr, *d_exp_tab = nullptr;
     int* d_species = nullptr;
@@ -152,8 +152,20 @@ void build_angles(rcm_solver* s) {
     d.csum = sum;
 }
 
+// The kernels read the ensemble-wide constants from ONE __constant__ bank per device.  Several solvers
+// on one device (tests, the two adapters) therefore take turns: whoever launches next re-uploads its
+// constants after the device has drained.  (The intended use is one solver per GPU.)
+const rcm_solver* g_const_owner[64] = {nullptr};
+
 int refresh_const(rcm_solver* s) {
+    const int dev = s->device & 63;
+    if (g_const_owner[dev] != s) {
+        CU(cudaDeviceSynchronize());
+        s->const_dirty = true;
+        g_const_owner[dev] = s;
+    }
     if (!s->const_dirty) return RCM_OK;
+    CU(cudaStreamSynchronize(s->stream));  // kernels in flight still read the old constants
     DevConst& d = s->dc;
     set_active_species(s);
     d.nactive = s->nactive;
@@ -260,7 +272,7 @@ CtaShape pick_shape(const rcm_solver* s, int ncol, int nsm) {
 int launch(rcm_solver* s, int mode, int nsteps, bool want_diag) {
     int st = refresh_const(s);
     if (st != RCM_OK) return st;
-    if (!s->has_table) return fail(s, RCM_ERR_STATE, "no lookup table loaded");
+    if (mode == MODE_RT ? !s->has_spectral : !s->has_table) return fail(s, RCM_ERR_STATE, "no lookup table loaded");
     if (s->ncol <= 0) return fail(s, RCM_ERR_STATE, "no columns loaded");
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, s->device);
@@ -359,6 +371,7 @@ int rcm_destroy(rcm_solver* s) {
     if (!s) return RCM_OK;
     cudaSetDevice(s->device);
     cudaStreamSynchronize(s->stream);
+    if (g_const_owner[s->device & 63] == s) g_const_owner[s->device & 63] = nullptr;
     void* ptrs[] = {s->d_xsec_file, s->d_coef, s->d_species, s->d_planck_c, s->d_planck_k, s->d_exp_tab, s->d_T, s->d_Ts, s->d_vmr, s->d_rh,
                     s->d_Tprev, s->d_time, s->d_lbl_lo, s->d_lbl_hi, s->d_lbl_tau5, s->d_lbl_h2o_ref, s->d_lbl_o3_ref, s->d_sH, s->d_sO,
                     s->d_dTstat, s->d_part, s->d_Ed, s->d_Eu, s->d_dE, s->d_dt, s->d_diag, s->d_scalars, s->d_tau,
@@ -430,6 +443,29 @@ int rcm_set_repwvl_table(rcm_solver* s, const double* xsec, const double* wvl, c
     CU(dalloc(s->d_xsec_file, n));
     CU(cudaMemcpy(s->d_xsec_file, xsec, n * sizeof(double), cudaMemcpyHostToDevice));
     s->coef_dirty = true;
+    {
+        int st = rcm_set_spectral_grid(s, wvl, weight, n_wvl);
+        if (st != RCM_OK) return st;
+    }
+    s->p_grid.assign(p_grid, p_grid + n_p);
+    s->t_ref.assign(t_ref, t_ref + n_p);
+    s->t_pert.assign(t_pert, t_pert + n_tpert);
+    s->dc.nwvl = n_wvl;
+    s->dc.n_tpert = n_tpert;
+    s->dc.n_species = n_species;
+    s->dc.n_p = n_p;
+    for (int m = 0; m < n_tpert; ++m) s->dc.t_pert[m] = t_pert[m];
+    s->has_table = true;
+    s->lbl_mode = false;
+    s->const_dirty = true;
+    s->tau_valid = false;
+    s->tau_cap = 0;
+    return RCM_OK;
+}
+
+int rcm_set_spectral_grid(rcm_solver* s, const double* wvl, const double* weight, int n_wvl) {
+    if (!s || !wvl || !weight || n_wvl < 1) return RCM_ERR_ARG;
+    CU(cudaSetDevice(s->device));
     // Planck factors that depend on the wavelength alone (main.cpp:188-191):
     //   B = w*2*h*c^2 / (lambda^5 * (exp(h*c/(lambda*kB*T)) - 1)) / 1e9
     const double h = 6.62607e-34, c = 299792458, kB = 1.380649e-23;  // main.cpp:70-72
@@ -443,21 +479,17 @@ int rcm_set_repwvl_table(rcm_solver* s, const double* xsec, const double* wvl, c
     CU(dalloc(s->d_planck_k, (size_t)n_wvl));
     CU(cudaMemcpy(s->d_planck_c, pc.data(), n_wvl * sizeof(double), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(s->d_planck_k, pk.data(), n_wvl * sizeof(double), cudaMemcpyHostToDevice));
-    s->p_grid.assign(p_grid, p_grid + n_p);
-    s->t_ref.assign(t_ref, t_ref + n_p);
-    s->t_pert.assign(t_pert, t_pert + n_tpert);
     s->wvl.assign(wvl, wvl + n_wvl);
     s->weight.assign(weight, weight + n_wvl);
+    if (s->dc.nwvl != n_wvl) {  // a cross-section table of another size can no longer be used
+        s->has_table = false;
+        s->tau_cap = 0;
+    }
     s->dc.nwvl = n_wvl;
-    s->dc.n_tpert = n_tpert;
-    s->dc.n_species = n_species;
-    s->dc.n_p = n_p;
-    for (int m = 0; m < n_tpert; ++m) s->dc.t_pert[m] = t_pert[m];
-    s->has_table = true;
+    s->has_spectral = true;
     s->lbl_mode = false;
     s->const_dirty = true;
     s->tau_valid = false;
-    s->tau_cap = 0;
     return RCM_OK;
 }
 
@@ -575,7 +607,7 @@ int rcm_build_tau(rcm_solver* s, double* tau_out, int* lowpos_p, int* lowpos_t) 
 
 int rcm_radiative_transfer(rcm_solver* s, const double* tau, double* E_down, double* E_up, double* dE) {
     if (!s) return RCM_ERR_ARG;
-    if (!s->has_table || s->ncol <= 0) return fail(s, RCM_ERR_STATE, "table and columns must be loaded");
+    if (!s->has_spectral || s->ncol <= 0) return fail(s, RCM_ERR_STATE, "spectral grid and columns must be loaded");
     CU(cudaSetDevice(s->device));
     int st = ensure_tau(s);
     if (st != RCM_OK) return st;
