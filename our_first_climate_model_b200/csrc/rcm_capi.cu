@@ -22,8 +22,10 @@ struct rcm_solver {
     DevConst dc{};
     bool const_dirty = true;
     int opt_angle_cubes = 1;
-    int opt_config = 3;        // 0: 512 threads x 64 columns, 1: 256 threads x 32 columns (2 CTAs/SM), 2: 384x64, 3: 192x32
-    int opt_stagger = 0;       // de-phasing delay in cycles (0 = off)
+    int opt_config = 0;        // 0: planned (plan_parts); k > 0: force kShapes[k-1] for the whole ensemble
+        // prepare the next wavelength inside the angle loop (0: separate phase)
+    double tau_clamp = 240.0;  // set by build_angles
+    int clampk = 1;
     // table
     bool has_table = false, has_spectral = false;
     std::vector<double> p_grid, t_ref, t_pert, wvl, weight;
@@ -96,60 +98,63 @@ void set_active_species(rcm_solver* s) {
 // Angle schedule.  Quadrature nodes mu_i = dmu/2 + dmu*i (main.cpp:482) = (2i+1)/(2*nangle).  With
 // n = 2i+1, 1/mu is proportional to 1/n, hence t(n/3) = t(n)^3: nodes are visited in chains
 // n, n/3, n/9, ... so that only the chain heads need an exp.  Summation order over angles
-// changes, values of mu do not.
+// changes, values of mu do not.  Also fixes tau_clamp / clampk (see exp_scaled in rcm_kernels.cu).
 void build_angles(rcm_solver* s) {
     DevConst& d = s->dc;
     const int na = s->p.nangle;
     const double dmu = 1.0 / (double)na;
     d.nangle = na;
-    // chains of node indices: head first, then the nodes reached by successive cubes
-    std::vector<std::vector<int>> chains;
+    std::vector<std::vector<int>> chains;  // node indices, head first
     if (s->opt_angle_cubes) {
         std::vector<char> used(na, 0);
         for (int i = na - 1; i >= 0; --i) {
             if (used[i]) continue;
             std::vector<int> ch;
-            int n = 2 * i + 1;
-            while (true) {
-                const int idx = (n - 1) / 2;
-                used[idx] = 1;
-                ch.push_back(idx);
+            for (int n = 2 * i + 1;; n /= 3) {
+                used[(n - 1) / 2] = 1;
+                ch.push_back((n - 1) / 2);
                 if (n % 3 != 0) break;
-                n /= 3;
             }
             chains.push_back(ch);
         }
     } else {
         for (int i = 0; i < na; ++i) chains.push_back({i});
     }
-    // deal the chains to the two streams, longest first, always to the shorter stream
-    std::stable_sort(chains.begin(), chains.end(),
-                     [](const std::vector<int>& a, const std::vector<int>& b) { return a.size() > b.size(); });
-    std::vector<int> order[2], cube[2];
-    for (const auto& ch : chains) {
-        const int k = order[1].size() < order[0].size() ? 1 : 0;
-        for (size_t m = 0; m < ch.size(); ++m) {
-            order[k].push_back(ch[m]);
-            cube[k].push_back(m ? 1 : 0);
+    if (chains.size() % 2) chains.push_back({-1});  // padding chain: exp(0) = 1 with zero quadrature weight
+    d.nchain = (int)chains.size();
+    double sum = 0.0, x_max = 0.0, x_min = 1e300;
+    int slot = 0;
+    for (int a = 0; a < MAX_ANGLE + 2; ++a) {
+        d.chain_len[a] = 1;
+        d.neg_inv_mu_l2e[a] = 0.0;
+        d.cmu[a] = 0.0;
+    }
+    for (int ic = 0; ic < d.nchain; ++ic) {
+        d.chain_len[ic] = (int)chains[ic].size();
+        for (size_t m = 0; m < chains[ic].size(); ++m, ++slot) {
+            if (chains[ic][m] < 0) continue;
+            const double mu = dmu / 2.0 + dmu * (double)chains[ic][m];  // main.cpp:482
+            d.cmu[slot] = 2 * M_PI * mu * dmu;
+            sum += d.cmu[slot];
+            if (m == 0) {
+                d.neg_inv_mu_l2e[ic] = (-1.0 / mu) * 92.33248261689366;  // times 64/ln2, see exp_scaled
+                x_max = std::max(x_max, 1.0 / mu);
+            }
+            x_min = std::min(x_min, 1.0 / mu);
         }
     }
-    d.nslot = (int)std::max(order[0].size(), order[1].size());
-    double sum = 0.0;
-    for (int k = 0; k < 2; ++k)
-        for (int a = 0; a < d.nslot; ++a) {
-            if (a < (int)order[k].size()) {
-                const double mu = dmu / 2.0 + dmu * (double)order[k][a];  // main.cpp:482
-                d.neg_inv_mu_l2e[k][a] = (-1.0 / mu) * 92.33248261689366;  // times 64/ln2, see exp_scaled
-                d.cmu[k][a] = 2 * M_PI * mu * dmu;
-                d.cube[k][a] = cube[k][a];
-                sum += d.cmu[k][a];
-            } else {  // padding slot: exp(0) = 1 with zero quadrature weight
-                d.neg_inv_mu_l2e[k][a] = 0.0;
-                d.cmu[k][a] = 0.0;
-                d.cube[k][a] = 0;
-            }
-        }
+    d.nslot = slot;
     d.csum = sum;
+    {
+        const double ec[5] = {0x1.5d87fe78a6731p-40, 0x1.3b2ab6fba4e77p-31, 0x1.c6b08d704a0c0p-23, 0x1.ebfbdff82c58fp-15,
+                              0x1.62e42fefa39efp-7};  // c^5/120, c^4/24, c^3/6, c^2/2, c with c = ln2/64
+        for (int k = 0; k < 5; ++k) d.expc[k] = ec[k];
+    }
+    // exp_scaled needs |tau/mu|/ln2 <= 1000 for every slot evaluated with exp.  Clamping tau once per layer
+    // guarantees that for free - provided the clamped transmission is still zero for every use
+    // (exp(-tau_clamp/mu_max) < 1e-40; the fluxes are O(100)).  Otherwise the kernel clamps inside exp.
+    s->tau_clamp = 999.0 * 0.6931471805599453 / x_max;
+    s->clampk = (s->tau_clamp * x_min > 92.2) ? 0 : 1;
 }
 
 // The kernels read the ensemble-wide constants from ONE __constant__ bank per device.  Several solvers
@@ -257,16 +262,39 @@ int ensure_tau(rcm_solver* s) {
     return RCM_OK;
 }
 
-// CTA shapes (columns per tile, threads, resident CTAs per SM).  Several small independent CTAs per SM
-// de-phase the latency-bound table phase of one CTA against the issue-bound angle loop of another.
-struct CtaShape { int C, nthreads, per_sm; };
-CtaShape pick_shape(const rcm_solver* s, int ncol, int nsm) {
-    static const CtaShape shapes[] = {{64, 512, 1}, {32, 256, 2}, {64, 384, 1}, {32, 192, 2}, {16, 128, 3}, {16, 96, 4}};
-    CtaShape sh = shapes[(s->opt_config >= 0 && s->opt_config < 6) ? s->opt_config : 3];
-    // small ensembles: more, smaller tiles so that every SM gets work
-    if ((ncol + sh.C - 1) / sh.C < nsm * sh.per_sm && sh.C > 16) sh = shapes[4];
-    if (rcm_step_smem_bytes(sh.C, s->nactive, sh.nthreads) * sh.per_sm > 227 * 1024) sh.per_sm = 1;
-    return sh;
+// CTA shapes: C columns per tile x 128 threads (2 halves x G = 64/C wavelength groups), three CTAs per SM.
+// Small CTAs keep the barrier domains small; the time of one tile is proportional to the wavelengths per thread,
+// ceil(nwvl / G).  `eff` is the measured relative efficiency of a shape at equal wavelength-rounds.
+struct CtaShape { int C, nthreads, per_sm; double eff; };
+const CtaShape kShapes[] = {{16, 128, 3, 1.0}, {8, 128, 3, 0.95}, {4, 128, 3, 0.89}, {32, 192, 2, 0.9}, {16, 96, 4, 0.93}};
+constexpr int kAutoShapes = 3;  // the first three are the ones the planner picks from
+
+struct Part { int col0, ncols; CtaShape sh; };
+
+double part_cost(const CtaShape& sh, int ncols, int nwvl, int nsm) {
+    if (ncols <= 0) return 0.0;
+    const long tiles = (ncols + sh.C - 1) / sh.C, slots = (long)nsm * sh.per_sm;
+    const long rounds = (tiles + slots - 1) / slots;
+    const int G = sh.nthreads / (2 * sh.C);
+    return (double)rounds * ((nwvl + G - 1) / G) / sh.eff;
+}
+
+// One launch covers the whole ensemble with one tile shape, so that every column sees the same order of
+// floating-point additions wherever it sits (replicated columns give bit-identical results).  Tiles are dealt
+// to the resident CTAs round-robin; for small ensembles narrower tiles put more SMs to work.
+// (Launching a partial last round separately with narrower tiles was measured: no gain - SMs whose CTAs have
+// finished leave the FP64 pipe to their neighbours' CTAs - and it breaks the bit-identity above.)
+int plan_parts(const rcm_solver* s, int ncol, int nsm, Part* parts) {
+    if (s->opt_config > 0 && s->opt_config <= 5) {  // forced shape (benchmarks, tests)
+        parts[0] = {0, ncol, kShapes[s->opt_config - 1]};
+        return 1;
+    }
+    const int nwvl = s->dc.nwvl;
+    CtaShape best = kShapes[0];
+    for (int k = 1; k < kAutoShapes; ++k)
+        if (part_cost(kShapes[k], ncol, nwvl, nsm) < part_cost(best, ncol, nwvl, nsm)) best = kShapes[k];
+    parts[0] = {0, ncol, best};
+    return 1;
 }
 
 int launch(rcm_solver* s, int mode, int nsteps, bool want_diag) {
@@ -276,36 +304,8 @@ int launch(rcm_solver* s, int mode, int nsteps, bool want_diag) {
     if (s->ncol <= 0) return fail(s, RCM_ERR_STATE, "no columns loaded");
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, s->device);
-    StepArgs a{};
-    a.ncol = s->ncol;
-    const CtaShape sh = pick_shape(s, s->ncol, nsm);
-    a.C = sh.C;
-    a.ntiles = (s->ncol + a.C - 1) / a.C;
-    a.nthreads = sh.nthreads;
-    a.stagger_mode = (sh.per_sm > 1) ? 1 : 0;
-    a.stagger_cycles = s->opt_stagger;
-    a.nsteps = nsteps;
-    a.step_index = s->step_index;
-    a.coef = s->d_coef;
-    a.planck_c = s->d_planck_c;
-    a.planck_k = s->d_planck_k;
-    a.Tlayer = s->d_T;
-    a.Tsurf = s->d_Ts;
-    a.vmr = s->d_vmr;
-    a.rel_hum = s->d_rh;
-    a.Tprev = s->d_Tprev;
-    a.time_h = s->d_time;
-    a.E_down = s->d_Ed;
-    a.E_up = s->d_Eu;
-    a.dE = s->d_dE;
-    a.dt = s->d_dt;
-    a.diag = want_diag ? s->d_diag : nullptr;
-    a.tau_io = s->d_tau;
-    a.lowpos_t = s->d_lowpos;
-    a.exp_tab = s->d_exp_tab;
-    a.h2o_slot = s->h2o_slot;
-    const int ctas = nsm * sh.per_sm;
-    const int grid = a.ntiles < ctas ? a.ntiles : ctas;
+    Part parts[2];
+    const int nparts = plan_parts(s, s->ncol, nsm, parts);
     std::pair<cudaEvent_t, cudaEvent_t> ev;
     if (!s->ev_free.empty()) {
         ev = s->ev_free.back();
@@ -315,10 +315,46 @@ int launch(rcm_solver* s, int mode, int nsteps, bool want_diag) {
         CU(cudaEventCreate(&ev.second));
     }
     CU(cudaEventRecord(ev.first, s->stream));
-    CU(rcm_launch_step(mode, a, s->nactive, grid, s->stream));
+    for (int ip = 0; ip < nparts; ++ip) {
+        const Part& p = parts[ip];
+        const size_t o = (size_t)p.col0;
+        StepArgs a{};
+        a.ncol = p.ncols;
+        a.diag_ncol = s->ncol;
+        a.C = p.sh.C;
+        a.ntiles = (p.ncols + a.C - 1) / a.C;
+        a.nthreads = p.sh.nthreads;
+        a.clampk = s->clampk;
+        a.tau_clamp = s->tau_clamp;
+        a.nsteps = nsteps;
+        a.step_index = s->step_index;
+        a.coef = s->d_coef;
+        a.planck_c = s->d_planck_c;
+        a.planck_k = s->d_planck_k;
+        a.Tlayer = s->d_T + o * NLAY;
+        a.Tsurf = s->d_Ts + o;
+        a.vmr = s->d_vmr + o * s->nactive * NLAY;
+        a.rel_hum = s->d_rh + o * NLAY;
+        a.Tprev = s->d_Tprev + o * NLAY;
+        a.time_h = s->d_time + o;
+        a.E_down = s->d_Ed + o * NLEV;
+        a.E_up = s->d_Eu + o * NLEV;
+        a.dE = s->d_dE + o * NLAY;
+        a.dt = s->d_dt + o;
+        a.diag = want_diag ? s->d_diag + o * 4 : nullptr;
+        a.tau_io = s->d_tau ? s->d_tau + o * s->dc.nwvl * NLAY : nullptr;
+        a.lowpos_t = s->d_lowpos + o * NLAY;
+        a.exp_tab = s->d_exp_tab;
+        a.h2o_slot = s->h2o_slot;
+        int per_sm = p.sh.per_sm;
+        if (rcm_step_smem_bytes(a.C, s->nactive, a.nthreads) * per_sm > 224 * 1024) per_sm = 1;
+        const int ctas = nsm * per_sm;
+        const int grid = a.ntiles < ctas ? a.ntiles : ctas;
+        CU(rcm_launch_step(mode, a, s->nactive, grid, s->stream));
+        s->launches += 1;
+    }
     CU(cudaEventRecord(ev.second, s->stream));
     if (mode == MODE_STEP) s->ev_used.push_back(ev); else s->ev_free.push_back(ev);
-    s->launches += 1;
     if (s->ev_used.size() >= 1024) {  // long runs: fold the finished timings so the pool stays small
         st = rcm_kernel_time_ms(s, 0, nullptr, nullptr);
         if (st != RCM_OK) return st;
@@ -355,8 +391,15 @@ int rcm_create(int device, const rcm_params* p, rcm_solver** out) {
         return RCM_ERR_CUDA;
     }
     s->stream = s->own_stream;
+    // 2^(j/64) with j << 14 pre-subtracted from the high word: exp_scaled adds k << 14 = (m << 20) + (j << 14)
     double tab[EXP_TAB];
-    for (int j = 0; j < EXP_TAB; ++j) tab[j] = std::exp2((double)j / EXP_TAB);
+    for (int j = 0; j < EXP_TAB; ++j) {
+        const double v = std::exp2((double)j / EXP_TAB);
+        unsigned long long bits;
+        std::memcpy(&bits, &v, 8);
+        bits -= (unsigned long long)j << (14 + 32);
+        std::memcpy(&tab[j], &bits, 8);
+    }
     if (dalloc(s->d_exp_tab, EXP_TAB) != cudaSuccess ||
         cudaMemcpy(s->d_exp_tab, tab, sizeof(tab), cudaMemcpyHostToDevice) != cudaSuccess) {
         delete s;
@@ -410,10 +453,6 @@ int rcm_set_option(rcm_solver* s, int option, int value) {
     }
     if (option == 1) {
         s->opt_config = value;
-        return RCM_OK;
-    }
-    if (option == 2) {
-        s->opt_stagger = value;
         return RCM_OK;
     }
     return fail(s, RCM_ERR_ARG, "unknown option");

@@ -10,12 +10,12 @@
 //   K4   spectral + angular reduction to E_down, E_up, heating dE          (main.cpp:326-341)
 //   K5b  adaptive time step, temperature update, surface temperature       (main.cpp:156-176)
 //
-// Mapping.  A CTA owns a tile of C consecutive columns for all fused steps.  Its 256 threads
-// are C columns x G wavelength groups: thread (c, g) walks wavelengths g, g+G, ... of column c,
-// so lanes of a warp hold the same wavelength for consecutive columns (table rows and Planck
-// constants are warp-uniform, per-column scalars come from shared memory without bank
-// conflicts).  The whole vertical problem of one (column, wavelength) lives in registers:
-// tau[20], source differences[21], transmissions[20] and the 41 flux accumulators.
+// Mapping.  A CTA owns a tile of C consecutive columns for all fused steps.  Its threads are
+// C columns x 2 halves x G wavelength groups: the lane pair (c, g) walks wavelengths g, g+G, ... of
+// column c, one lane per half of the atmosphere, so lanes of a warp hold the same wavelength for
+// consecutive columns (table rows and Planck constants are warp-uniform, per-column scalars come from
+// shared memory without bank conflicts).  The vertical problem of one (column, wavelength, half) lives in
+// registers: tau[10], source differences[10], two sets of transmissions[10], 20 flux accumulators.
 // The path is FP64-pipe bound: no tensor cores, HBM traffic ~1.6 KB per column-step.
 #include <cfloat>
 #include <cstdio>
@@ -33,39 +33,47 @@ namespace {
 // z = a*b*64/ln2 (the caller passes b already scaled by 64/ln2), k = round(z), f = z - k:
 //   exp = 2^(k>>6) * 2^((k&63)/64) * exp(f*ln2/64),  |f| <= 1/2,
 // exp(f*c) - 1 = f*h(f) with a degree-4 Horner h (truncation 3.5e-17 relative).
-// 9 FP64-pipe instructions + 6 integer/LDS instructions (CUDA's exp(): ~16 + 8).  The 64-entry
-// table 2^(j/64) is replicated per lane (tab[j*32 + lane]) so the LDS.64 never bank-conflicts.
-// The power of two is clamped at 2^-1000 (result ~1e-301, i.e. 0 for every use here); valid up
-// to exp(+700).
+// 9 FP64-pipe instructions + 4 others (LOP3, LEA, LDS.64, LEA).  Non-FP64 instructions are not free
+// next to DFMA on this GPU (tools/probe/issue_probe.cu: each costs ~0.75 issue cycles, a DFMA 2), hence:
+//  * the 64-entry table 2^(j/64) is replicated per lane (tab[j*32 + lane]): the LDS.64 never bank-conflicts;
+//  * the power of two is applied to the TABLE VALUE with one integer multiply-add on its high word,
+//    hi += k << 14.  Since k = 64 m + j, k << 14 = (m << 20) + (j << 14): the table entries are stored
+//    with j << 14 pre-subtracted from their high word (rcm_create), so no shift/mask of k is needed;
+//  * no clamp of the exponent: the caller guarantees |k >> 6| <= 1000 (tau is clamped once per layer,
+//    StepArgs::tau_clamp), unless CLAMPK, which clamps k here for angle schedules that need it.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ double exp_scaled(double a, double b_l2e64, const double* __restrict__ tab_lane) {
+template <bool CLAMPK>
+__device__ __forceinline__ double exp_scaled(double a, double b_l2e64, unsigned tab_lane) {
     const double SHIFT = 6755399441055744.0;  // 1.5 * 2^52: the add leaves round(z) in the low word
     const double t = fma(a, b_l2e64, SHIFT);
-    const int k = __double2loint(t);
+    int k = __double2loint(t);
     const double kd = t - SHIFT;
     const double f = fma(a, b_l2e64, -kd);  // exact product minus an integer: one rounding
-    const double T = tab_lane[(k & (EXP_TAB - 1)) << 5];
-    double h = fma(f, 0x1.5d87fe78a6731p-40, 0x1.3b2ab6fba4e77p-31);  // c^5/120, c^4/24   (c = ln2/64)
-    h = fma(f, h, 0x1.c6b08d704a0c0p-23);                              // c^3/6
-    h = fma(f, h, 0x1.ebfbdff82c58fp-15);                              // c^2/2
-    h = fma(f, h, 0x1.62e42fefa39efp-7);                               // c
+    if (CLAMPK) k = max(k, -64000);
+    double Ts;  // tab_lane: shared-window byte address of this lane's copy of entry 0 (entries are 256 B apart)
+    asm("{\n\t.reg .b32 j, ad;\n\tand.b32 j, %1, 63;\n\tmad.lo.u32 ad, j, 256, %2;\n\tld.shared.f64 %0, [ad];\n\t}"
+        : "=d"(Ts)
+        : "r"(k), "r"(tab_lane));
+    const double T = __hiloint2double(__double2hiint(Ts) + (k << 14), __double2loint(Ts));  // 2^(k/64)
+    // Horner coefficients c^5/120, c^4/24, c^3/6, c^2/2, c (c = ln2/64) come from the constant bank: as
+    // literals each block of ten exp's would re-materialise them into uniform registers (10 UMOV per block)
+    double h = fma(f, cst.expc[0], cst.expc[1]);
+    h = fma(f, h, cst.expc[2]);
+    h = fma(f, h, cst.expc[3]);
+    h = fma(f, h, cst.expc[4]);
     const double u = T * f;
-    const double y = fma(u, h, T);
-    const int m = max(k >> 6, -1000);
-    return __hiloint2double(__double2hiint(y) + (m << 20), __double2loint(y));
+    return fma(u, h, T);
 }
 
 constexpr double L2E64 = 0x1.71547652b82fep+6;  // 64/ln2
 
-// a / d for normal, finite d: hardware reciprocal seed (20 bits) + two Newton steps + one residual
-// correction of the quotient (<= 1 ulp).  7 FP64-pipe instructions, no special-case branches
+// a / d for normal, finite d: hardware reciprocal seed (>= 20 bits) + one Newton step (40 bits) + one
+// residual correction of the quotient (<= 1 ulp).  5 FP64-pipe instructions, no special-case branches
 // (the IEEE division routine costs ~45 instructions with its slow-path checks).
 __device__ __forceinline__ double div_fast(double a, double d) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
-    double e = fma(-d, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-d, r, 1.0);
+    const double e = fma(-d, r, 1.0);
     r = fma(r, e, r);
     const double q = a * r;
     return fma(fma(-d, q, a), r, q);
@@ -105,12 +113,16 @@ __device__ __forceinline__ int lowerpos_t(double tref, double x, int n) {
 // layer and sweep; the angle-independent parts sum_mu cmu*B (and main.cpp:302) are added up front.
 // Lane h=0 runs the down sweep through its layers 0..9 while lane h=1 runs the up sweep through 19..10;
 // they swap the radiance at level 10 and each finishes the other's sweep through its own layers.  Both
-// lanes execute identical code.  Two angles (streams A and B of the schedule) are carried at once:
-// their dependency chains are independent, which doubles the instruction-level parallelism.
+// lanes execute identical code.
+// The angle loop is software-pipelined by hand: while the two dependent 10-step recurrences of one angle
+// run (latency-bound on their own), the ten independent transmissions of the next chain head are evaluated
+// in the same basic block, so a warp always has independent FP64 work in flight.  Two register sets
+// ping-pong (loop over chains unrolled by two); cubes are taken in place.
 // ------------------------------------------------------------------------------------------
+template <bool CLAMPK>
 __device__ __forceinline__ void sweep_item(const double (&tau)[HALF], const double (&Bo)[HALF], double Bs, int h,
-                                           const double* __restrict__ tab_lane, double (&E1)[HALF],
-                                           double (&E2)[HALF], double& Eu20) {
+                                           unsigned tab_lane, double (&E1)[HALF], double (&E2)[HALF],
+                                           double& Eu20) {
     double D1[HALF], Dx, X0;
     {
         const double Bnb = __shfl_xor_sync(0xffffffffu, Bo[HALF - 1], 1);  // partner's boundary layer
@@ -127,58 +139,50 @@ __device__ __forceinline__ void sweep_item(const double (&tau)[HALF], const doub
         X0 = Bstart - Bo[0];
         Eu20 = fma(cs, Bstart, Eu20);  // main.cpp:302 summed over the angles (h=1 only)
     }
-    const int nslot = cst.nslot;
-    double tA[HALF], tB[HALF];
-    for (int is = 0; is < nslot; ++is) {
-        const double cmA = cst.cmu[0][is], cmB = cst.cmu[1][is];
-        const int kind = cst.cube[0][is] | (cst.cube[1][is] << 1);
-        const double nimA = cst.neg_inv_mu_l2e[0][is], nimB = cst.neg_inv_mu_l2e[1][is];
-        if (kind == 0) {
-#pragma unroll
-            for (int j = 0; j < HALF; ++j) {
-                tA[j] = exp_scaled(tau[j], nimA, tab_lane);
-                tB[j] = exp_scaled(tau[j], nimB, tab_lane);
-            }
-        } else if (kind == 1) {  // 1/mu of slot A is three times its previous slot's: t <- t^3
-#pragma unroll
-            for (int j = 0; j < HALF; ++j) {
-                tA[j] = tA[j] * tA[j] * tA[j];
-                tB[j] = exp_scaled(tau[j], nimB, tab_lane);
-            }
-        } else if (kind == 2) {
-#pragma unroll
-            for (int j = 0; j < HALF; ++j) {
-                tA[j] = exp_scaled(tau[j], nimA, tab_lane);
-                tB[j] = tB[j] * tB[j] * tB[j];
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < HALF; ++j) {
-                tA[j] = tA[j] * tA[j] * tA[j];
-                tB[j] = tB[j] * tB[j] * tB[j];
-            }
-        }
-        double XA = X0, XB = X0;
+    // both sweeps of one angle with the transmissions tc
+    auto sweep = [&](const double (&tc)[HALF], double cm) {
+        double X = X0;
 #pragma unroll
         for (int j = 0; j < HALF; ++j) {
-            XA = fma(tA[j], XA, D1[j]);
-            XB = fma(tB[j], XB, D1[j]);
-            E1[j] = fma(cmA, XA, E1[j]);
-            E1[j] = fma(cmB, XB, E1[j]);
+            X = fma(tc[j], X, D1[j]);
+            E1[j] = fma(cm, X, E1[j]);
         }
-        double YA = __shfl_xor_sync(0xffffffffu, XA, 1);
-        double YB = __shfl_xor_sync(0xffffffffu, XB, 1);
+        double Y = __shfl_xor_sync(0xffffffffu, X, 1);
 #pragma unroll
         for (int j = HALF - 1; j >= 1; --j) {
-            YA = fma(tA[j], YA, -D1[j - 1]);
-            YB = fma(tB[j], YB, -D1[j - 1]);
-            E2[j] = fma(cmA, YA, E2[j]);
-            E2[j] = fma(cmB, YB, E2[j]);
+            Y = fma(tc[j], Y, -D1[j - 1]);
+            E2[j] = fma(cm, Y, E2[j]);
         }
-        YA = fma(tA[0], YA, Dx);
-        YB = fma(tB[0], YB, Dx);
-        E2[0] = fma(cmA, YA, E2[0]);
-        E2[0] = fma(cmB, YB, E2[0]);
+        Y = fma(tc[0], Y, Dx);
+        E2[0] = fma(cm, Y, E2[0]);
+    };
+    // One chain of angles mu, mu/3, mu/9, ...: the head's transmissions tc were produced during the previous
+    // chain; every further level is the cube of the one before (in place).  While the last level is swept,
+    // the transmissions of the NEXT chain's head are evaluated into tn (ten independent exp's that fill
+    // the issue slots the two dependent recurrences leave empty).
+    int slot = 0;
+    auto chain = [&](double (&tc)[HALF], double (&tn)[HALF], int ic) {
+        const int len = cst.chain_len[ic];
+        for (int k = 1; k < len; ++k) {
+            sweep(tc, cst.cmu[slot++]);
+#pragma unroll
+            for (int j = 0; j < HALF; ++j) tc[j] = tc[j] * tc[j] * tc[j];
+        }
+        const double nim = cst.neg_inv_mu_l2e[ic + 1];
+#pragma unroll
+        for (int j = 0; j < HALF; ++j) tn[j] = exp_scaled<CLAMPK>(tau[j], nim, tab_lane);
+        sweep(tc, cst.cmu[slot++]);
+    };
+    const int nchain = cst.nchain;  // even (a zero-weight exp(0) chain pads an odd count)
+    double tA[HALF], tB[HALF];
+    {
+        const double nim = cst.neg_inv_mu_l2e[0];
+#pragma unroll
+        for (int j = 0; j < HALF; ++j) tA[j] = exp_scaled<CLAMPK>(tau[j], nim, tab_lane);
+    }
+    for (int ic = 0; ic < nchain; ic += 2) {
+        chain(tA, tB, ic);
+        chain(tB, tA, ic + 1);
     }
 }
 
@@ -193,29 +197,35 @@ struct Smem {
     double* T;        // [20][C] layer temperature (sorted), rows in pair order
     double* invT;     // [20][C]
     double* delT;     // [20][C]
-    double* dE;       // [20][C]   natural layer order
     double* vmr;      // [nactive][20][C]
-    double* Ep;       // [21][NT/2] reduction staging
-    double* Ed;       // [21][C]   natural level order
-    double* Eu;       // [21][C]
     double* Ts;       // [C]
     double* invTs;    // [C]
     double* dt;       // [C]
     int* it;          // [20][C]
+    double* Ep;       // [21][NT/2] reduction staging
+    double* Ed;       // [21][C]   natural level order
+    double* Eu;       // [21][C]
+    double* dE;       // [20][C]   natural layer order
+    static constexpr size_t REGION = (size_t)NLEV * (NT / 2) + 2 * (size_t)NLEV * C + (size_t)NLAY * C;
+    static size_t bytes(int nactive) {
+        return ((size_t)EXP_TAB * 32 + 3 * (size_t)NLAY * C + (size_t)nactive * NLAY * C + 3 * (size_t)C +
+                REGION) * sizeof(double) + (size_t)NLAY * C * sizeof(int);
+    }
     __device__ __forceinline__ Smem(unsigned char* base, int nactive) {
         double* p = reinterpret_cast<double*>(base);
         exp_tab = p; p += EXP_TAB * 32;
         T = p;       p += NLAY * C;
         invT = p;    p += NLAY * C;
         delT = p;    p += NLAY * C;
-        dE = p;      p += NLAY * C;
         vmr = p;     p += nactive * NLAY * C;
-        Ep = p;      p += NLEV * (NT / 2);
-        Ed = p;      p += NLEV * C;
-        Eu = p;      p += NLEV * C;
         Ts = p;      p += C;
         invTs = p;   p += C;
         dt = p;      p += C;
+        Ep = p;
+        Ed = Ep + NLEV * (NT / 2);
+        Eu = Ed + NLEV * C;
+        dE = Eu + NLEV * C;
+        p += REGION;
         it = reinterpret_cast<int*>(p);
     }
 };
@@ -235,8 +245,10 @@ __device__ __forceinline__ void prep_tau_indices(const Smem<C, NT>& s, int tid) 
     }
 }
 
-template <int MODE, int NACT, int C, int NT>
-__global__ void __launch_bounds__(NT, (NT == 256 || NT == 512) ? 512 / NT : 384 / NT) rcm_step_kernel(const StepArgs a) {
+constexpr int min_ctas(int NT) { return (NT == 256 || NT == 512) ? 512 / NT : 384 / NT; }  // 168 registers per thread
+
+template <int MODE, int NACT, int C, int NT, bool CLAMPK>
+__global__ void __launch_bounds__(NT, min_ctas(NT)) rcm_step_kernel(const StepArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int G = NT / (2 * C);  // wavelength groups
     const int tid = threadIdx.x, lane = tid & 31;
@@ -246,7 +258,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 || NT == 512) ? 512 / NT : 384 
     const int sb = h * HALF * C + c;  // this thread's row block in the per-layer arrays
 
     for (int i = tid; i < EXP_TAB * 32; i += NT) s.exp_tab[i] = a.exp_tab[i >> 5];
-    const double* tab_lane = s.exp_tab + lane;
+    const unsigned tab_lane = (unsigned)__cvta_generic_to_shared(s.exp_tab + lane);
     const int nwvl = cst.nwvl;
 
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
@@ -266,6 +278,43 @@ __global__ void __launch_bounds__(NT, (NT == 256 || NT == 512) ? 512 / NT : 384 
         }
         if (tid < C) s.Ts[tid] = (tid < ncl) ? a.Tsurf[col0 + tid] : 250.0;
         __syncthreads();
+
+        // K1 for one owned layer j (local index) and wavelength w: bilinear (p,T) interpolation of the cross
+        // sections in the reference's operation order, no FMA contraction -> tau is bit-identical to
+        // read_tau's for identical inputs.  The four bilinear coefficients c0, cT, cP, cPT
+        // (repwvl_thermal.cpp:235-238) depend on the table alone and are precomputed per cell (rcm_coef_kernel).
+        auto tau_cell = [&](int j, int w) -> double {
+            const int r = h * HALF + j;
+            const double dT = s.delT[sb + j * C], dP = cst.delP[r];
+            const int cell = cst.ipcell[r] + s.it[sb + j * C];
+            const double2* cf = reinterpret_cast<const double2*>(a.coef) + (size_t)(cell * nwvl + w) * 2 * nact;
+            double acc = 0.0;
+#pragma unroll
+            for (int k = 0; k < (NACT > 0 ? NACT : RCM_NSPECIES); ++k) {
+                if (NACT == 0 && k >= nact) break;
+                // two 128-bit loads (one 256-bit LDG.E.ENL2.256 was measured 8% slower for the whole step)
+                const double2 c0T = __ldg(cf + 2 * k), cPPT = __ldg(cf + 2 * k + 1);
+                double v = __dadd_rn(c0T.x, __dmul_rn(c0T.y, dT));
+                v = __dadd_rn(v, __dmul_rn(cPPT.x, dP));
+                v = __dadd_rn(v, __dmul_rn(__dmul_rn(cPPT.y, dT), dP));
+                acc = __dadd_rn(acc, __dmul_rn(v, s.vmr[k * NLAY * C + sb + j * C]));
+            }
+            acc = __dmul_rn(acc, cst.numDens[r]);
+            if (cst.cloud_row == r) acc = __dadd_rn(acc, cst.cloud_tau);  // main.cpp:270
+            return acc;
+        };
+        // tau of owned layer j at wavelength w as the transmissions will use it (w is clamped by the caller)
+        auto tau_use = [&](int j, int w) -> double {
+            double v;
+            if (MODE == MODE_RT) {
+                const int l = h ? (NLAY - 1 - j) : j;
+                v = live ? a.tau_io[((size_t)(col0 + c) * nwvl + w) * NLAY + l] : 0.0;
+            } else {
+                v = tau_cell(j, w);
+            }
+            if (!CLAMPK) v = fmin(v, a.tau_clamp);  // exp(-tau_clamp/mu) ~ 1e-100: same fluxes, see exp_scaled
+            return v;
+        };
 
         for (int step = 0; step < a.nsteps; ++step) {
             const bool first = (MODE == MODE_STEP) && (a.step_index + step == 0);
@@ -320,89 +369,53 @@ __global__ void __launch_bounds__(NT, (NT == 256 || NT == 512) ? 512 / NT : 384 
             for (int i = tid; i < NLAY * C; i += NT) s.invT[i] = 1.0 / s.T[i];
             if (tid < C) s.invTs[tid] = 1.0 / s.Ts[tid];
             __syncthreads();
-            if (MODE == MODE_TAU && a.lowpos_t) {
-                for (int i = tid; i < NLAY * C; i += NT) {
-                    const int l = i / C, cc = i % C;
-                    if (cc < ncl) a.lowpos_t[(size_t)(col0 + cc) * NLAY + (NLAY - 1 - l)] = s.it[prow(l) * C + cc];
+
+            if (MODE == MODE_TAU) {  // K1 alone: the compute part of read_tau + cloud_into_tau
+                if (a.lowpos_t) {
+                    for (int i = tid; i < NLAY * C; i += NT) {
+                        const int l = i / C, cc = i % C;
+                        if (cc < ncl)
+                            a.lowpos_t[(size_t)(col0 + cc) * NLAY + (NLAY - 1 - l)] = s.it[prow(l) * C + cc];
+                    }
                 }
+                for (int w = g; w < nwvl; w += G) {
+#pragma unroll
+                    for (int j = 0; j < HALF; ++j) {
+                        const double t = tau_cell(j, w);
+                        const int l = h ? (NLAY - 1 - j) : j;
+                        if (live) a.tau_io[((size_t)(col0 + c) * nwvl + w) * NLAY + l] = t;
+                    }
+                }
+                continue;
             }
 
             // ---------------- K1-K4: per (column, wavelength, half) work in registers -----------
             // E1[j]: flux of the first sweep  (h=0: E_down[j+1],   h=1: E_up[19-j])
             // E2[j]: flux of the second sweep (h=0: E_up[j],       h=1: E_down[20-j])
             double E1[HALF], E2[HALF], Eu20 = 0.0;
-            int coff[HALF];  // offset (in double2) of this column's table cell per owned layer: independent of w
 #pragma unroll
-            for (int j = 0; j < HALF; ++j) {
-                E1[j] = E2[j] = 0.0;
-                coff[j] = (MODE == MODE_RT) ? 0 : (cst.ipcell[h * HALF + j] + s.it[sb + j * C]) * nwvl * 2 * nact;
-            }
-
-            if (MODE == MODE_STEP && a.stagger_cycles > 0) {
-                // De-phase the warps: every second wavelength group (or CTA) starts half an item later, so its
-                // latency-bound tau/Planck phase overlaps the issue-bound angle loop of the others.
-                const bool late = (a.stagger_mode == 0) ? (g & 1) : (blockIdx.x & 1);
-                if (late && (a.stagger_mode == 0 || (step == 0 && tile == (int)blockIdx.x))) {
-                    const long long t0 = clock64();
-                    while (clock64() - t0 < a.stagger_cycles) {
-                    }
-                }
-            }
-            for (int w = g; w < nwvl; w += G) {
-                double tau[HALF];
-                // K1: bilinear (p,T) interpolation of the cross sections in the reference's operation
-                // order, no FMA contraction -> tau is bit-identical to read_tau's for identical inputs.
-                // The four bilinear coefficients c0, cT, cP, cPT (repwvl_thermal.cpp:235-238) depend on
-                // the table alone and are precomputed per cell (rcm_coef_kernel).
-                if (MODE == MODE_RT) {
+            for (int j = 0; j < HALF; ++j) E1[j] = E2[j] = 0.0;
+            // Every thread runs the same number of wavelength items, so the loop and the shuffles inside are
+            // provably warp-uniform: a thread whose last item does not exist (w >= nwvl) repeats the last
+            // wavelength with a zero Planck factor, which adds exactly 0 to every flux.
+            const int nitem = (nwvl + G - 1) / G;
+#pragma unroll 1
+            for (int item = 0; item < nitem; ++item) {
+                const int w_any = g + item * G;
+                const bool real = w_any < nwvl;
+                const int w = real ? w_any : nwvl - 1;
+                double tau[HALF], Bo[HALF];
 #pragma unroll
-                    for (int j = 0; j < HALF; ++j) {
-                        const int l = h ? (NLAY - 1 - j) : j;
-                        tau[j] = live ? a.tau_io[((size_t)(col0 + c) * nwvl + w) * NLAY + l] : 0.0;
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < HALF; ++j) {
-                        const int r = h * HALF + j;
-                        const double dT = s.delT[sb + j * C], dP = cst.delP[r];
-                        const double2* cf = reinterpret_cast<const double2*>(a.coef) + (coff[j] + w * 2 * nact);
-                        double acc = 0.0;
-#pragma unroll
-                        for (int k = 0; k < (NACT > 0 ? NACT : RCM_NSPECIES); ++k) {
-                            if (NACT == 0 && k >= nact) break;
-                            const double2 c0T = __ldg(cf + 2 * k), cPPT = __ldg(cf + 2 * k + 1);
-                            double v = __dadd_rn(c0T.x, __dmul_rn(c0T.y, dT));
-                            v = __dadd_rn(v, __dmul_rn(cPPT.x, dP));
-                            v = __dadd_rn(v, __dmul_rn(__dmul_rn(cPPT.y, dT), dP));
-                            acc = __dadd_rn(acc, __dmul_rn(v, s.vmr[k * NLAY * C + sb + j * C]));
-                        }
-                        acc = __dmul_rn(acc, cst.numDens[r]);
-                        if (cst.cloud_row == r) acc = __dadd_rn(acc, cst.cloud_tau);  // main.cpp:270
-                        tau[j] = acc;
-                    }
-                    if (MODE == MODE_TAU) {
-                        if (live) {
-#pragma unroll
-                            for (int j = 0; j < HALF; ++j) {
-                                const int l = h ? (NLAY - 1 - j) : j;
-                                a.tau_io[((size_t)(col0 + c) * nwvl + w) * NLAY + l] = tau[j];
-                            }
-                        }
-                        continue;
-                    }
-                }
-
-                // K2: Planck source B_l = k_w / (exp(c_w / T_l) - 1) (main.cpp:188-191 regrouped so that
-                // everything that depends on the wavelength alone is precomputed on the host).
-                const double pc = __ldg(a.planck_c + w), pk = __ldg(a.planck_k + w);
-                double Bo[HALF];
+                for (int j = 0; j < HALF; ++j) tau[j] = tau_use(j, w);
+                // K2: Planck source B = k_w / (exp(c_w / T) - 1) (main.cpp:188-191 regrouped so that everything
+                // that depends on the wavelength alone is precomputed on the host); surface: main.cpp:301
+                const double pc = __ldg(a.planck_c + w), pk = real ? __ldg(a.planck_k + w) : 0.0;
 #pragma unroll
                 for (int j = 0; j < HALF; ++j)
-                    Bo[j] = div_fast(pk, exp_scaled(pc, s.invT[sb + j * C] * L2E64, tab_lane) - 1.0);
-                const double Bs = div_fast(pk, exp_scaled(pc, s.invTs[c] * L2E64, tab_lane) - 1.0);  // main.cpp:301
-                sweep_item(tau, Bo, Bs, h, tab_lane, E1, E2, Eu20);
+                    Bo[j] = div_fast(pk, exp_scaled<false>(pc, s.invT[sb + j * C] * L2E64, tab_lane) - 1.0);
+                const double Bs = div_fast(pk, exp_scaled<false>(pc, s.invTs[c] * L2E64, tab_lane) - 1.0);
+                sweep_item<CLAMPK>(tau, Bo, Bs, h, tab_lane, E1, E2, Eu20);
             }
-            if (MODE == MODE_TAU) continue;
 
             // ---------------- K4: reduce the G wavelength groups of every column ---------------
             constexpr int GC = G * C;
@@ -462,7 +475,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 || NT == 512) ? 512 / NT : 384 
                     const int col = col0 + tid;
                     a.time_h[col] += (float)dt / 3600;  // main.cpp:581
                     if (a.diag) {
-                        double* dg = a.diag + ((size_t)step * a.ncol + col) * 4;
+                        double* dg = a.diag + ((size_t)step * a.diag_ncol + col) * 4;
                         dg[0] = cst.solar_irr - s.Eu[tid];
                         dg[1] = dT_stat;
                         dg[2] = mabs;
@@ -578,7 +591,7 @@ __global__ void __launch_bounds__(256) rcm_microbench_kernel(double* out, long i
     __shared__ double stab[EXP_TAB * 32];
     for (int i = threadIdx.x; i < EXP_TAB * 32; i += blockDim.x) stab[i] = tab[i >> 5];
     __syncthreads();
-    const double* tl = stab + (threadIdx.x & 31);
+    const unsigned tl = (unsigned)__cvta_generic_to_shared(stab + (threadIdx.x & 31));
     double v[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) v[k] = -1.0 - 0.001 * (threadIdx.x + k);
@@ -589,7 +602,7 @@ __global__ void __launch_bounds__(256) rcm_microbench_kernel(double* out, long i
             if (WHICH == 0) v[k] = fma(v[k], a, b);
             if (WHICH == 1) v[k] = exp(v[k]) - 1.5;
             if (WHICH == 2) v[k] = -1.0 / v[k] - 1.7;
-            if (WHICH == 3) v[k] = exp_scaled(v[k], L2E64, tl) - 1.5;
+            if (WHICH == 3) v[k] = exp_scaled<false>(v[k], L2E64, tl) - 1.5;
         }
     }
     double sacc = 0;
@@ -709,7 +722,7 @@ __global__ void __launch_bounds__(NT, 384 / NT) rcm_lbl_rt_kernel(const LblArgs 
     const int h = tid & 1, q = tid >> 1, c = q % C, g = q / C;
     const int sb = h * HALF * C + c;
     for (int i = tid; i < EXP_TAB * 32; i += NT) s_tab[i] = a.exp_tab[i >> 5];
-    const double* tab_lane = s_tab + lane;
+    const unsigned tab_lane = (unsigned)__cvta_generic_to_shared(s_tab + lane);
     const int tile = blockIdx.x % a.ntiles, chunk = blockIdx.x / a.ntiles;
     const int col0 = tile * C, ncl = min(C, a.ncol - col0);
     for (int i = tid; i < NLAY * C; i += NT) {
@@ -745,7 +758,7 @@ __global__ void __launch_bounds__(NT, 384 / NT) rcm_lbl_rt_kernel(const LblArgs 
             Bo[j] = cplkavg_dev(lo, hi, s_T[sb + j * C]);
         }
         const double Bs = cplkavg_dev(lo, hi, s_Ts[c]);
-        sweep_item(tau, Bo, Bs, h, tab_lane, E1, E2, Eu20);
+        sweep_item<true>(tau, Bo, Bs, h, tab_lane, E1, E2, Eu20);
     }
     // partial fluxes of this wavelength chunk: part[chunk][col][0..20] = E_down, [21..41] = E_up
     double* part = a.part + ((size_t)chunk * a.ncol + col0) * 42;
@@ -830,15 +843,18 @@ __global__ void rcm_cplkavg_kernel(int n, const double* lo, const double* hi, co
 }  // namespace
 
 size_t rcm_step_smem_bytes(int C, int nactive, int nthreads) {
-    size_t d = (size_t)EXP_TAB * 32 + (size_t)NLAY * C * 4 + (size_t)nactive * NLAY * C +
-               (size_t)NLEV * (nthreads / 2) + (size_t)NLEV * C * 2 + (size_t)C * 3;
-    return d * sizeof(double) + (size_t)NLAY * C * sizeof(int);
+    if (C == 16 && nthreads == 128) return Smem<16, 128>::bytes(nactive);
+    if (C == 8 && nthreads == 128) return Smem<8, 128>::bytes(nactive);
+    if (C == 4 && nthreads == 128) return Smem<4, 128>::bytes(nactive);
+    if (C == 32 && nthreads == 192) return Smem<32, 192>::bytes(nactive);
+    if (C == 16 && nthreads == 96) return Smem<16, 96>::bytes(nactive);
+    return 0;
 }
 
 template <int MODE, int NACT, int C, int NT>
 static cudaError_t launch_t(const StepArgs& a, int nactive, int grid, cudaStream_t st) {
-    const size_t smem = rcm_step_smem_bytes(C, nactive, NT);
-    auto kern = rcm_step_kernel<MODE, NACT, C, NT>;
+    const size_t smem = Smem<C, NT>::bytes(nactive);
+    auto kern = a.clampk ? rcm_step_kernel<MODE, NACT, C, NT, true> : rcm_step_kernel<MODE, NACT, C, NT, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, NT, smem, st>>>(a);
@@ -848,20 +864,15 @@ static cudaError_t launch_t(const StepArgs& a, int nactive, int grid, cudaStream
 template <int MODE>
 static cudaError_t launch_m(const StepArgs& a, int nactive, int grid, cudaStream_t st) {
     const bool five = (nactive == 5);
-    if (a.C == 64 && a.nthreads == 512)
-        return five ? launch_t<MODE, 5, 64, 512>(a, nactive, grid, st) : launch_t<MODE, 0, 64, 512>(a, nactive, grid, st);
-    if (a.C == 32 && a.nthreads == 256)
-        return five ? launch_t<MODE, 5, 32, 256>(a, nactive, grid, st) : launch_t<MODE, 0, 32, 256>(a, nactive, grid, st);
-    if (a.C == 64 && a.nthreads == 384)
-        return five ? launch_t<MODE, 5, 64, 384>(a, nactive, grid, st) : launch_t<MODE, 0, 64, 384>(a, nactive, grid, st);
-    if (a.C == 32 && a.nthreads == 192)
-        return five ? launch_t<MODE, 5, 32, 192>(a, nactive, grid, st) : launch_t<MODE, 0, 32, 192>(a, nactive, grid, st);
-    if (a.C == 16 && a.nthreads == 128)
-        return five ? launch_t<MODE, 5, 16, 128>(a, nactive, grid, st) : launch_t<MODE, 0, 16, 128>(a, nactive, grid, st);
-    if (a.C == 16 && a.nthreads == 96)
-        return five ? launch_t<MODE, 5, 16, 96>(a, nactive, grid, st) : launch_t<MODE, 0, 16, 96>(a, nactive, grid, st);
-    if (a.C == 16 && a.nthreads == 512)
-        return five ? launch_t<MODE, 5, 16, 512>(a, nactive, grid, st) : launch_t<MODE, 0, 16, 512>(a, nactive, grid, st);
+#define RCM_SHAPE(CC, TT)                  \
+    if (a.C == CC && a.nthreads == TT)     \
+        return five ? launch_t<MODE, 5, CC, TT>(a, nactive, grid, st) : launch_t<MODE, 0, CC, TT>(a, nactive, grid, st);
+    RCM_SHAPE(16, 128)
+    RCM_SHAPE(8, 128)
+    RCM_SHAPE(4, 128)
+    RCM_SHAPE(32, 192)
+    RCM_SHAPE(16, 96)
+#undef RCM_SHAPE
     return cudaErrorInvalidValue;
 }
 

@@ -10,7 +10,6 @@ constexpr int NLAY = RCM_NLAYER;
 constexpr int NLEV = RCM_NLEVEL;
 constexpr int MAX_ANGLE = 64;
 constexpr int MAX_TPERT = 16;
-constexpr int RCM_THREADS = 512;   // threads per CTA of the step kernel (4 warps per SM sub-partition)
 constexpr int HALF = NLAY / 2;     // layers owned by each lane of a pair
 constexpr int EXP_TAB = 64;        // entries of the 2^(j/64) table used by the solver's exp
 
@@ -28,24 +27,27 @@ struct DevConst {
     int cloud_row;     // pair-order row of the cloud layer, -1 if none
     double delP[NLAY], numDens[NLAY], tref_ip[NLAY], player[NLAY], conv[NLAY];
     double t_pert[MAX_TPERT];
-    // angle schedule: slot a holds quadrature node n_a (1/mu = 2*nangle/n_a ... see capi) either
-    // evaluated with exp (head) or derived by cubing the transmissions of the previous slot
-    // The nodes are dealt to two streams that the kernel advances together (nslot slots each).
-    int nslot;
-    double neg_inv_mu_l2e[2][MAX_ANGLE / 2];  // -1/mu of the slot, times 64/ln2 (argument scaling of exp_scaled)
-    double cmu[2][MAX_ANGLE / 2];             // 2*pi*mu*dmu of the slot (0 for a padding slot)
-    int cube[2][MAX_ANGLE / 2];               // 1: t <- t^3 from the stream's previous slot, 0: exp
-    double csum;                              // sum of cmu over all nodes
+    // Angle schedule.  The quadrature nodes are visited in chains mu, mu/3, mu/9, ...: the head of a chain
+    // is evaluated with exp, every further level is the cube of the one before (1/mu triples).  Slots are
+    // numbered chain by chain.  nchain is even (a zero-weight exp(0) chain pads an odd count); entry
+    // [nchain] of neg_inv_mu_l2e is 0 (the pipelined loop evaluates it and never uses the result).
+    int nslot, nchain;
+    int chain_len[MAX_ANGLE + 2];          // slots of chain i (>= 1)
+    double neg_inv_mu_l2e[MAX_ANGLE + 2];  // per CHAIN: -1/mu of its head, times 64/ln2 (argument scaling of exp_scaled)
+    double cmu[MAX_ANGLE + 2];             // per SLOT: 2*pi*mu*dmu (0 for a padding slot)
+    double csum;                           // sum of cmu over all nodes
+    double expc[5];                        // Horner coefficients of exp_scaled
     // LBL band edges etc. live in global memory
 };
 
 // Per-launch arguments (pointers into the solver's device allocations).
 struct StepArgs {
-    int ncol;            // columns in this launch
+    int ncol;            // columns in this launch (all pointers below are offset to its first column)
+    int diag_ncol;       // columns of the whole ensemble = row length of diag
     int C;               // columns per tile
     int nthreads;        // threads per CTA (2 * C * wavelength groups)
-    int stagger_mode;    // 0: odd wavelength groups start late every tile-step, 1: odd CTAs start late once
-    long long stagger_cycles;
+    int clampk;          // 1: exp_scaled clamps its exponent itself (angle schedules where tau_clamp would bite)
+    double tau_clamp;    // tau is clamped to this before the transmissions are evaluated (see exp_scaled)
     int ntiles;
     int nsteps;          // time steps fused in this launch
     long step_index;     // global index of the first step (0 => initial-profile tau, main.cpp:500-504)
