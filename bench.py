@@ -35,9 +35,10 @@ UNIT = "updates/s"
 # expression tree: 31 exp, 33 divides, ~520 add/mul/fma.
 ALG_EXP, ALG_DIV, ALG_FMA = 31, 33, 520
 # FP64-pipe instructions this repo's kernel really executes per unit, and DRAM bytes per column-step:
-# from the ncu capture committed under profiles/ (see profiles/README.md); None = not measured yet.
-EXEC_FP64_PER_UNIT = 391.0
-DRAM_BYTES_PER_COLUMN_STEP = 1666.0
+# from the ncu capture committed under profiles/ (r1b_ncu_step_kernel_regions.md: 1,636,892,672 FP64 warp
+# instructions and 85.9 + 25.1 MB of DRAM traffic for one launch of 65,536 columns x 100 wavelengths x 20 layers).
+EXEC_FP64_PER_UNIT = 399.6
+DRAM_BYTES_PER_COLUMN_STEP = 1694.0
 
 
 def _env_int(name, default):
@@ -289,7 +290,7 @@ def run_b200(args, rank, world, local_rank):
                              "126 MB L2 and the kernel is FP64-pipe bound (DRAM < 1% of peak)"},
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1e3 * e2e_s / args.steps, "api": "rcm_step_host (pinned host buffers)",
+                    "ms_per_step": 1e3 * e2e_s / args.steps, "api": "rcm_step_host (pinned host buffers; columns travel in 8 chunks through 3 streams, copies overlap the step)",
                     "check_olr_col0": olr_check},
             "gpu_launches": launches, "clocks": clocks, "fp64_peaks_Gops": peaks}
     print(json.dumps(line), flush=True)

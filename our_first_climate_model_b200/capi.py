@@ -380,6 +380,17 @@ class Solver:
         _check(_lib.rcm_step_host(self._h, *[C.c_void_p(x) for x in (T_in, Ts_in, vmr_in, Ed, Eu, dE, T_out, Ts_out)]),
                self._h)
 
+    def step_host(self, Tlayer, Tsurf, vmr_active) -> dict:
+        """rcm_step_host with numpy arrays: upload T / Tsurf / active VMRs, one step, download the results."""
+        n = self.ncol
+        T, Ts, v = _f64(Tlayer), _f64(Tsurf), _f64(vmr_active)
+        assert T.shape == (n, NLAY) and Ts.shape == (n,) and v.shape == (n, self.nactive, NLAY)
+        out = dict(E_down=np.zeros((n, NLEV)), E_up=np.zeros((n, NLEV)), dE=np.zeros((n, NLAY)),
+                   Tlayer=np.zeros((n, NLAY)), Tsurf=np.zeros(n))
+        _check(_lib.rcm_step_host(self._h, _p(T), _p(Ts), _p(v), _p(out["E_down"]), _p(out["E_up"]), _p(out["dE"]),
+                                  _p(out["Tlayer"]), _p(out["Tsurf"])), self._h)
+        return out
+
     def cplkavg_device(self, lo, hi, t):
         lo, hi, t = _f64(lo), _f64(hi), _f64(t)
         out = np.zeros_like(lo)

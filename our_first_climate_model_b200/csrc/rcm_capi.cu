@@ -57,6 +57,8 @@ struct rcm_solver {
     std::string err;
     long launches = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_free, ev_used;
+    cudaStream_t pipe_stream[3] = {nullptr, nullptr, nullptr};  // rcm_step_host's chunk pipeline
+    cudaEvent_t pipe_done[3] = {nullptr, nullptr, nullptr}, pipe_start = nullptr;
     double kt_ms = 0.0;
     long kt_n = 0;
 };
@@ -297,13 +299,58 @@ int plan_parts(const rcm_solver* s, int ncol, int nsm, Part* parts) {
     return 1;
 }
 
+int nsm_of(const rcm_solver* s) {
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, s->device);
+    return nsm;
+}
+
+// One kernel launch for the columns [p.col0, p.col0 + p.ncols) on stream st.
+int launch_part(rcm_solver* s, int mode, int nsteps, bool want_diag, const Part& p, int nsm, cudaStream_t st) {
+    const size_t o = (size_t)p.col0;
+    StepArgs a{};
+    a.ncol = p.ncols;
+    a.diag_ncol = s->ncol;
+    a.C = p.sh.C;
+    a.ntiles = (p.ncols + a.C - 1) / a.C;
+    a.nthreads = p.sh.nthreads;
+    a.clampk = s->clampk;
+    a.tau_clamp = s->tau_clamp;
+    a.nsteps = nsteps;
+    a.step_index = s->step_index;
+    a.coef = s->d_coef;
+    a.planck_c = s->d_planck_c;
+    a.planck_k = s->d_planck_k;
+    a.Tlayer = s->d_T + o * NLAY;
+    a.Tsurf = s->d_Ts + o;
+    a.vmr = s->d_vmr + o * s->nactive * NLAY;
+    a.rel_hum = s->d_rh + o * NLAY;
+    a.Tprev = s->d_Tprev + o * NLAY;
+    a.time_h = s->d_time + o;
+    a.E_down = s->d_Ed + o * NLEV;
+    a.E_up = s->d_Eu + o * NLEV;
+    a.dE = s->d_dE + o * NLAY;
+    a.dt = s->d_dt + o;
+    a.diag = want_diag ? s->d_diag + o * 4 : nullptr;
+    a.tau_io = s->d_tau ? s->d_tau + o * s->dc.nwvl * NLAY : nullptr;
+    a.lowpos_t = s->d_lowpos + o * NLAY;
+    a.exp_tab = s->d_exp_tab;
+    a.h2o_slot = s->h2o_slot;
+    int per_sm = p.sh.per_sm;
+    if (rcm_step_smem_bytes(a.C, s->nactive, a.nthreads) * per_sm > 224 * 1024) per_sm = 1;
+    const int ctas = nsm * per_sm;
+    const int grid = a.ntiles < ctas ? a.ntiles : ctas;
+    CU(rcm_launch_step(mode, a, s->nactive, grid, st));
+    s->launches += 1;
+    return RCM_OK;
+}
+
 int launch(rcm_solver* s, int mode, int nsteps, bool want_diag) {
     int st = refresh_const(s);
     if (st != RCM_OK) return st;
     if (mode == MODE_RT ? !s->has_spectral : !s->has_table) return fail(s, RCM_ERR_STATE, "no lookup table loaded");
     if (s->ncol <= 0) return fail(s, RCM_ERR_STATE, "no columns loaded");
-    int nsm = 148;
-    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, s->device);
+    const int nsm = nsm_of(s);
     Part parts[2];
     const int nparts = plan_parts(s, s->ncol, nsm, parts);
     std::pair<cudaEvent_t, cudaEvent_t> ev;
@@ -316,42 +363,8 @@ int launch(rcm_solver* s, int mode, int nsteps, bool want_diag) {
     }
     CU(cudaEventRecord(ev.first, s->stream));
     for (int ip = 0; ip < nparts; ++ip) {
-        const Part& p = parts[ip];
-        const size_t o = (size_t)p.col0;
-        StepArgs a{};
-        a.ncol = p.ncols;
-        a.diag_ncol = s->ncol;
-        a.C = p.sh.C;
-        a.ntiles = (p.ncols + a.C - 1) / a.C;
-        a.nthreads = p.sh.nthreads;
-        a.clampk = s->clampk;
-        a.tau_clamp = s->tau_clamp;
-        a.nsteps = nsteps;
-        a.step_index = s->step_index;
-        a.coef = s->d_coef;
-        a.planck_c = s->d_planck_c;
-        a.planck_k = s->d_planck_k;
-        a.Tlayer = s->d_T + o * NLAY;
-        a.Tsurf = s->d_Ts + o;
-        a.vmr = s->d_vmr + o * s->nactive * NLAY;
-        a.rel_hum = s->d_rh + o * NLAY;
-        a.Tprev = s->d_Tprev + o * NLAY;
-        a.time_h = s->d_time + o;
-        a.E_down = s->d_Ed + o * NLEV;
-        a.E_up = s->d_Eu + o * NLEV;
-        a.dE = s->d_dE + o * NLAY;
-        a.dt = s->d_dt + o;
-        a.diag = want_diag ? s->d_diag + o * 4 : nullptr;
-        a.tau_io = s->d_tau ? s->d_tau + o * s->dc.nwvl * NLAY : nullptr;
-        a.lowpos_t = s->d_lowpos + o * NLAY;
-        a.exp_tab = s->d_exp_tab;
-        a.h2o_slot = s->h2o_slot;
-        int per_sm = p.sh.per_sm;
-        if (rcm_step_smem_bytes(a.C, s->nactive, a.nthreads) * per_sm > 224 * 1024) per_sm = 1;
-        const int ctas = nsm * per_sm;
-        const int grid = a.ntiles < ctas ? a.ntiles : ctas;
-        CU(rcm_launch_step(mode, a, s->nactive, grid, s->stream));
-        s->launches += 1;
+        st = launch_part(s, mode, nsteps, want_diag, parts[ip], nsm, s->stream);
+        if (st != RCM_OK) return st;
     }
     CU(cudaEventRecord(ev.second, s->stream));
     if (mode == MODE_STEP) s->ev_used.push_back(ev); else s->ev_free.push_back(ev);
@@ -423,6 +436,11 @@ int rcm_destroy(rcm_solver* s) {
         if (q) cudaFree(q);
     for (auto& e : s->ev_free) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     for (auto& e : s->ev_used) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    for (int i = 0; i < 3; ++i) {
+        if (s->pipe_stream[i]) cudaStreamDestroy(s->pipe_stream[i]);
+        if (s->pipe_done[i]) cudaEventDestroy(s->pipe_done[i]);
+    }
+    if (s->pipe_start) cudaEventDestroy(s->pipe_start);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     delete s;
     return RCM_OK;
@@ -773,13 +791,71 @@ int rcm_get_state(rcm_solver* s, double* Tlayer, double* Tsurf, double* h2o, flo
     return RCM_OK;
 }
 
+// Host buffers in, one step, host buffers out.  For big repwvl ensembles the columns are cut into chunks that
+// travel through three internal streams: while chunk k is stepped, chunk k+1 is on its way up and chunk k-1 on
+// its way down (separate copy engines), so the call costs about one step plus one chunk of copies instead of
+// step + all copies.  Every chunk is launched with the tile shape of the whole ensemble: results are
+// bit-identical to rcm_update_columns + rcm_advance + rcm_get_state.
 int rcm_step_host(rcm_solver* s, const double* Tlayer_in, const double* Tsurf_in, const double* vmr_active_in,
                   double* E_down, double* E_up, double* dE, double* Tlayer_out, double* Tsurf_out) {
-    int st = rcm_update_columns(s, Tlayer_in, Tsurf_in, vmr_active_in);
+    if (!s) return RCM_ERR_ARG;
+    const int nchunk = (s && !s->lbl_mode && s->has_table) ? std::min(8, s->ncol / 4096) : 0;
+    if (nchunk < 2) {
+        int st = rcm_update_columns(s, Tlayer_in, Tsurf_in, vmr_active_in);
+        if (st != RCM_OK) return st;
+        st = rcm_advance_async(s, 1, nullptr);
+        if (st != RCM_OK) return st;
+        return rcm_get_state(s, Tlayer_out, Tsurf_out, nullptr, nullptr, E_down, E_up, dE, nullptr);
+    }
+    CU(cudaSetDevice(s->device));
+    int st = ensure_diag(s, 1);
     if (st != RCM_OK) return st;
-    st = rcm_advance_async(s, 1, nullptr);
+    st = refresh_const(s);
     if (st != RCM_OK) return st;
-    return rcm_get_state(s, Tlayer_out, Tsurf_out, nullptr, nullptr, E_down, E_up, dE, nullptr);
+    if (!s->pipe_stream[0]) {
+        for (int i = 0; i < 3; ++i) {
+            CU(cudaStreamCreateWithFlags(&s->pipe_stream[i], cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&s->pipe_done[i], cudaEventDisableTiming));
+        }
+        CU(cudaEventCreateWithFlags(&s->pipe_start, cudaEventDisableTiming));
+    }
+    const int nsm = nsm_of(s);
+    Part whole[2];
+    plan_parts(s, s->ncol, nsm, whole);
+    const int C = whole[0].sh.C;
+    const int per = ((s->ncol + nchunk - 1) / nchunk + C - 1) / C * C;  // chunk = whole tiles
+    CU(cudaEventRecord(s->pipe_start, s->stream));
+    for (int i = 0; i < 3; ++i) CU(cudaStreamWaitEvent(s->pipe_stream[i], s->pipe_start, 0));
+    const size_t D = sizeof(double);
+    const int na = s->nactive;
+    for (int k = 0, c0 = 0; c0 < s->ncol; ++k, c0 += per) {
+        const int n = std::min(per, s->ncol - c0);
+        const size_t o = (size_t)c0;
+        cudaStream_t q = s->pipe_stream[k % 3];
+        if (Tlayer_in) CU(cudaMemcpyAsync(s->d_T + o * NLAY, Tlayer_in + o * NLAY, n * NLAY * D, cudaMemcpyHostToDevice, q));
+        if (Tsurf_in) CU(cudaMemcpyAsync(s->d_Ts + o, Tsurf_in + o, n * D, cudaMemcpyHostToDevice, q));
+        if (vmr_active_in)
+            CU(cudaMemcpyAsync(s->d_vmr + o * na * NLAY, vmr_active_in + o * na * NLAY, (size_t)n * na * NLAY * D,
+                               cudaMemcpyHostToDevice, q));
+        const Part p{c0, n, whole[0].sh};
+        st = launch_part(s, MODE_STEP, 1, true, p, nsm, q);
+        if (st != RCM_OK) return st;
+        if (E_down) CU(cudaMemcpyAsync(E_down + o * NLEV, s->d_Ed + o * NLEV, n * NLEV * D, cudaMemcpyDeviceToHost, q));
+        if (E_up) CU(cudaMemcpyAsync(E_up + o * NLEV, s->d_Eu + o * NLEV, n * NLEV * D, cudaMemcpyDeviceToHost, q));
+        if (dE) CU(cudaMemcpyAsync(dE + o * NLAY, s->d_dE + o * NLAY, n * NLAY * D, cudaMemcpyDeviceToHost, q));
+        if (Tlayer_out) CU(cudaMemcpyAsync(Tlayer_out + o * NLAY, s->d_T + o * NLAY, n * NLAY * D, cudaMemcpyDeviceToHost, q));
+        if (Tsurf_out) CU(cudaMemcpyAsync(Tsurf_out + o, s->d_Ts + o, n * D, cudaMemcpyDeviceToHost, q));
+    }
+    for (int i = 0; i < 3; ++i) {
+        CU(cudaEventRecord(s->pipe_done[i], s->pipe_stream[i]));
+        CU(cudaStreamWaitEvent(s->stream, s->pipe_done[i], 0));
+    }
+    CU(rcm_launch_reduce_diag(s->d_diag, 1, s->ncol, s->p.dT_converged, s->d_scalars, s->stream));
+    s->launches += 1;
+    s->step_index += 1;
+    s->tau_valid = false;
+    CU(cudaStreamSynchronize(s->stream));
+    return RCM_OK;
 }
 
 int rcm_cplkavg_device(rcm_solver* s, int n, const double* lo_nm, const double* hi_nm, const double* t, double* out) {

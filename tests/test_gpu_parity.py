@@ -173,6 +173,31 @@ def test_full_size_properties(solver, rcm, golden):
     assert np.all(np.isfinite(st["Tlayer"]))
 
 
+def test_step_host_chunk_pipeline_is_bit_identical_to_the_resident_path(solver, rcm, golden):
+    """rcm_step_host (host buffers, chunked copy/compute pipeline) == set_columns + advance + get_state, bit for bit,
+    over two consecutive steps (the second one exercises the i > 0 branch: feedback + tau rebuild)."""
+    atm = rcm.read_atm(table_path(100).replace("Reduced100Forcing.rcmtab", "column21.atm"))
+    pl = atm[:, 1]
+    ncol = 20000                                  # not a multiple of the chunk or tile size
+    Tlev, vlev = rcm.make_ensemble(ncol, 77, pl, atm[:, 2], atm[:, 4:9].T.copy())
+    st0 = rcm.init_columns(pl, Tlev, vlev)
+    Ts0 = np.full(ncol, 288.2)
+    solver.set_repwvl_table_from(rcm.Table(table_path(100)))
+    solver.set_columns(pl, st0["Tlayer"], Ts0, st0["vmr9"], st0["rel_hum"])
+    solver.advance(1)
+    a1 = solver.get_state()
+    solver.advance(1)
+    a2 = solver.get_state()
+    active = [k for k in range(9) if solver.params.species_mask >> k & 1]
+    solver.set_columns(pl, st0["Tlayer"], Ts0, st0["vmr9"], st0["rel_hum"])
+    b1 = solver.step_host(st0["Tlayer"], Ts0, st0["vmr9"][:, active, :])
+    vmr1 = st0["vmr9"][:, active, :].copy()       # H2O after step 1 is unchanged (feedback acts from the 2nd iteration)
+    b2 = solver.step_host(b1["Tlayer"], b1["Tsurf"], vmr1)
+    for k in ("E_down", "E_up", "dE", "Tlayer", "Tsurf"):
+        assert np.array_equal(a1[k], b1[k]), k
+        assert np.array_equal(a2[k], b2[k]), k
+
+
 def test_cplkavg_device_matches_reference(solver, golden_misc):
     m = golden_misc
     out = solver.cplkavg_device(m["cpl_lo"], m["cpl_hi"], m["cpl_T"])
