@@ -181,6 +181,14 @@ int rcm_advance(rcm_solver* s, int nsteps, rcm_step_scalars* scalars_out);
  * *d_scalars -> device double[nsteps][4] (layout of rcm_step_scalars), valid until the next call. */
 int rcm_advance_async(rcm_solver* s, int nsteps, double** d_scalars);
 
+/* The RCE driver loop: iterate main.cpp:531-583 until the ensemble is stationary.  Advances in blocks of
+ * `check_every` fused steps (one launch each) and stops after the first block whose last step moved every
+ * column's sorted temperature profile by less than params.dT_converged (n_converged == ncol), or after
+ * max_steps.  *last = scalars of the last step done, *steps_done = iterations run by this call (either may be
+ * NULL).  One GPU; for N ranks use the same loop with an allreduce of the scalars between the blocks
+ * (our_first_climate_model_b200/distributed.py: run_to_equilibrium). */
+int rcm_run_to_equilibrium(rcm_solver* s, long max_steps, int check_every, rcm_step_scalars* last, long* steps_done);
+
 /* Download state / last-step fluxes; any pointer may be NULL.  Tlayer [ncol][20], Tsurf [ncol],
  * h2o [ncol][20], time_h [ncol] (float hours, main.cpp:581), E_down/E_up [ncol][21],
  * dE [ncol][20], dt [ncol]. */

@@ -359,6 +359,13 @@ class Solver:
             return None
         return np.array([[s.toa_net_sum, s.max_dT, s.n_converged, s.max_abs_dE] for s in sc])
 
+    def run_to_equilibrium(self, max_steps: int, check_every: int = 100):
+        """rcm_run_to_equilibrium -> (steps done, scalars of the last step [toa_net_sum, max_dT, n_converged, max|dE|])."""
+        last, done = StepScalars(), C.c_long(0)
+        _check(_lib.rcm_run_to_equilibrium(self._h, C.c_long(max_steps), C.c_int(check_every), C.byref(last),
+                                           C.byref(done)), self._h)
+        return done.value, np.array([last.toa_net_sum, last.max_dT, last.n_converged, last.max_abs_dE])
+
     def advance_async(self, nsteps: int) -> int:
         """Launch without waiting; returns the device address of double[nsteps][4] scalars."""
         ptr = C.c_void_p()

@@ -24,6 +24,7 @@ struct rcm_solver {
     int opt_angle_cubes = 1;
     int opt_config = 0;        // 0: planned (plan_parts); k > 0: force kShapes[k-1] for the whole ensemble
         // prepare the next wavelength inside the angle loop (0: separate phase)
+    int opt_cplk_narrow = 0;   // rcm_cplkavg_device evaluates the LBL kernel's narrow-band variant (tests)
     double tau_clamp = 240.0;  // set by build_angles
     int clampk = 1;
     // table
@@ -473,6 +474,10 @@ int rcm_set_option(rcm_solver* s, int option, int value) {
         s->opt_config = value;
         return RCM_OK;
     }
+    if (option == 2) {
+        s->opt_cplk_narrow = value ? 1 : 0;
+        return RCM_OK;
+    }
     return fail(s, RCM_ERR_ARG, "unknown option");
 }
 
@@ -695,13 +700,13 @@ static int lbl_advance(rcm_solver* s, int nsteps) {
     }
     LblArgs a{};
     a.ncol = s->ncol;
-    a.ntiles = (s->ncol + 31) / 32;
+    a.ntiles = (s->ncol + RCM_LBL_C - 1) / RCM_LBL_C;
     a.nwvl = s->lbl_nwvl;
     // enough (tile, wavelength chunk) CTAs to fill the GPU a few times over; chunk length a multiple of 3 groups
-    int nchunks = (4 * 296 + a.ntiles - 1) / a.ntiles;
+    int nchunks = (4 * 444 + a.ntiles - 1) / a.ntiles;
     if (nchunks > a.nwvl / 48) nchunks = a.nwvl / 48;
     if (nchunks < 1) nchunks = 1;
-    a.chunk_len = ((a.nwvl + nchunks - 1) / nchunks + 2) / 3 * 3;
+    a.chunk_len = ((a.nwvl + nchunks - 1) / nchunks + 3) / 4 * 4;  // a multiple of the 4 wavelength groups
     a.nchunks = (a.nwvl + a.chunk_len - 1) / a.chunk_len;
     const size_t need = (size_t)a.nchunks * n * 42;
     if (need > s->part_cap) {
@@ -714,6 +719,8 @@ static int lbl_advance(rcm_solver* s, int nsteps) {
     for (int k = 0; k < s->nactive; ++k)
         if (s->species[k] == 2) a.o3_slot = k;
     a.co2_factor = s->lbl_co2_factor;
+    a.clampk = s->clampk;
+    a.tau_clamp = s->tau_clamp;
     a.wvl_lo = s->d_lbl_lo;
     a.wvl_hi = s->d_lbl_hi;
     a.tau5 = s->d_lbl_tau5;
@@ -764,6 +771,23 @@ int rcm_advance(rcm_solver* s, int nsteps, rcm_step_scalars* scalars_out) {
         CU(cudaMemcpyAsync(scalars_out, s->d_scalars, (size_t)nsteps * sizeof(rcm_step_scalars), cudaMemcpyDeviceToHost,
                            s->stream));
         CU(cudaStreamSynchronize(s->stream));
+    }
+    return RCM_OK;
+}
+
+int rcm_run_to_equilibrium(rcm_solver* s, long max_steps, int check_every, rcm_step_scalars* last, long* steps_done) {
+    if (!s || max_steps <= 0 || check_every <= 0) return RCM_ERR_ARG;
+    if (steps_done) *steps_done = 0;
+    std::vector<rcm_step_scalars> sc((size_t)check_every);
+    long done = 0;
+    while (done < max_steps) {
+        const int n = (int)std::min<long>(check_every, max_steps - done);
+        const int st = rcm_advance(s, n, sc.data());
+        if (st != RCM_OK) return st;
+        done += n;
+        if (last) *last = sc[n - 1];
+        if (steps_done) *steps_done = done;
+        if (sc[n - 1].n_converged >= (double)s->ncol) break;
     }
     return RCM_OK;
 }
@@ -866,7 +890,7 @@ int rcm_cplkavg_device(rcm_solver* s, int n, const double* lo_nm, const double* 
     cudaError_t e = cudaMemcpyAsync(d, lo_nm, n * sizeof(double), cudaMemcpyHostToDevice, s->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d + n, hi_nm, n * sizeof(double), cudaMemcpyHostToDevice, s->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d + 2 * (size_t)n, t, n * sizeof(double), cudaMemcpyHostToDevice, s->stream);
-    if (e == cudaSuccess) e = rcm_launch_cplkavg(n, d, d + n, d + 2 * (size_t)n, d + 3 * (size_t)n, s->stream);
+    if (e == cudaSuccess) e = rcm_launch_cplkavg(n, d, d + n, d + 2 * (size_t)n, d + 3 * (size_t)n, s->d_exp_tab, s->opt_cplk_narrow, s->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, d + 3 * (size_t)n, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
     cudaFree(d);

@@ -667,6 +667,33 @@ __device__ __noinline__ double cplkavg_dev(double wvllo, double wvlhi, double t)
     return ans * (sigdpi * t4);
 }
 
+// The same function for the LBL kernel's inner loop.  LBL bins are narrow ((hi-lo)/hi < 1e-2), which is the
+// Simpson branch (cplkavg.cpp:155-182): 2 + 1 + 3 evaluations of x^3/(exp(x)-1), converged at n = 2.  Here
+// with the solver's exp (exp_scaled, <= 1 ulp like libm's) and division (div_fast, <= 1 ulp) instead of the
+// library routines, and with the two wavenumbers 1e7/lambda taken once per wavelength by the caller; every other
+// case goes to cplkavg_dev.  Same control flow and summation order, results within a few ulp of it.
+__device__ __forceinline__ double cplkavg_narrow(double wvllo, double wvlhi, double whi, double wlo, double t,
+                                                 unsigned tab_lane) {
+    const double c2 = 1.438786, sigma = 5.67032E-8, pi = 3.14159265358979323846;
+    const double vmax = 709.782712893384, sigdpi = sigma / pi, conc = 15. / (pi * pi * pi * pi);
+    const double v0 = div_fast(c2 * wlo, t), v1 = div_fast(c2 * whi, t);
+    if (!(t >= 1.e-4 && whi > wlo && wlo >= 0. && v0 > DBL_EPSILON && v1 < vmax && (whi - wlo) / whi < 1.e-2))
+        return cplkavg_dev(wvllo, wvlhi, t);
+    auto f = [&](double x) { return div_fast(x * x * x, exp_scaled<false>(x, L2E64, tab_lane) - 1.); };
+    const double hh = v1 - v0, ends = f(v0) + f(v1);
+    const double t4 = (t * t) * (t * t);
+    double prev = 0., val = 0.;
+    for (int n = 1; n <= 10; ++n) {
+        const double del = hh / (2 * n);
+        val = ends;
+        for (int k = 1; k <= 2 * n - 1; ++k) val += (double)(2 * (1 + k % 2)) * f(v0 + (double)k * del);
+        val *= del * (1. / 3.);
+        if (fabs((val - prev) / val) <= 1.e-6) break;
+        prev = val;
+    }
+    return sigdpi * t4 * conc * val;
+}
+
 // ------------------------------------------------------------------------------------------
 // Line-by-line path (BASELINE configs 3 and 5).  The reference ships the table format
 // (lbl.arts/README:5-16), the reader and cplkavg() but no driver; the composition below is the one
@@ -707,7 +734,7 @@ __global__ void __launch_bounds__(128) rcm_lbl_prep_kernel(const LblArgs a) {
     a.dTstat[col] = dmax;
 }
 
-template <int C, int NT>
+template <int C, int NT, bool CLAMPK>
 __global__ void __launch_bounds__(NT, 384 / NT) rcm_lbl_rt_kernel(const LblArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int G = NT / (2 * C), GC = G * C;
@@ -739,11 +766,18 @@ __global__ void __launch_bounds__(NT, 384 / NT) rcm_lbl_rt_kernel(const LblArgs 
     double E1[HALF], E2[HALF], Eu20 = 0.0;
 #pragma unroll
     for (int j = 0; j < HALF; ++j) E1[j] = E2[j] = 0.0;
-    const int w_lo = chunk * a.chunk_len, w_hi = min(a.nwvl, w_lo + a.chunk_len);
+    // chunk_len is a multiple of G: every thread runs chunk_len / G items (uniform trip count, see the step
+    // kernel); items beyond the last wavelength repeat it with a zero source.
+    const int w_lo = chunk * a.chunk_len;
     const size_t plane = (size_t)a.nwvl * NLAY;
-    for (int w = w_lo + g; w < w_hi; w += G) {
+#pragma unroll 1
+    for (int item = 0; item < a.chunk_len / G; ++item) {
+        const int w_any = w_lo + g + item * G;
+        const bool real = w_any < a.nwvl;
+        const int w = real ? w_any : a.nwvl - 1;
         double tau[HALF], Bo[HALF];
         const double lo = __ldg(a.wvl_lo + w), hi = __ldg(a.wvl_hi + w);
+        const double whi = 1.0E7 / lo, wlo = 1.0E7 / hi;  // cplkavg.cpp:141-142, once per wavelength
         const double* t5 = a.tau5 + (size_t)w * NLAY;
 #pragma unroll
         for (int j = 0; j < HALF; ++j) {
@@ -754,11 +788,12 @@ __global__ void __launch_bounds__(NT, 384 / NT) rcm_lbl_rt_kernel(const LblArgs 
             v = __dadd_rn(v, __ldg(t5 + 3 * plane + l));
             v = __dadd_rn(v, __ldg(t5 + 4 * plane + l));
             if (cst.cloud_row == h * HALF + j) v = __dadd_rn(v, cst.cloud_tau);
-            tau[j] = v;
-            Bo[j] = cplkavg_dev(lo, hi, s_T[sb + j * C]);
+            tau[j] = CLAMPK ? v : fmin(v, a.tau_clamp);
+            const double B = cplkavg_narrow(lo, hi, whi, wlo, s_T[sb + j * C], tab_lane);
+            Bo[j] = real ? B : 0.0;
         }
-        const double Bs = cplkavg_dev(lo, hi, s_Ts[c]);
-        sweep_item<true>(tau, Bo, Bs, h, tab_lane, E1, E2, Eu20);
+        const double Bsurf = cplkavg_narrow(lo, hi, whi, wlo, s_Ts[c], tab_lane);
+        sweep_item<CLAMPK>(tau, Bo, real ? Bsurf : 0.0, h, tab_lane, E1, E2, Eu20);
     }
     // partial fluxes of this wavelength chunk: part[chunk][col][0..20] = E_down, [21..41] = E_up
     double* part = a.part + ((size_t)chunk * a.ncol + col0) * 42;
@@ -835,9 +870,14 @@ __global__ void __launch_bounds__(128) rcm_lbl_finish_kernel(const LblArgs a) {
     }
 }
 
-__global__ void rcm_cplkavg_kernel(int n, const double* lo, const double* hi, const double* t, double* out) {
+__global__ void __launch_bounds__(256) rcm_cplkavg_kernel(int n, const double* lo, const double* hi, const double* t,
+                                                          double* out, const double* tab, int narrow) {
+    __shared__ double stab[EXP_TAB * 32];
+    for (int i = threadIdx.x; i < EXP_TAB * 32; i += blockDim.x) stab[i] = tab[i >> 5];
+    __syncthreads();
+    const unsigned tl = (unsigned)__cvta_generic_to_shared(stab + (threadIdx.x & 31));
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        out[i] = cplkavg_dev(lo[i], hi[i], t[i]);
+        out[i] = narrow ? cplkavg_narrow(lo[i], hi[i], 1.0E7 / lo[i], 1.0E7 / hi[i], t[i], tl) : cplkavg_dev(lo[i], hi[i], t[i]);
 }
 
 }  // namespace
@@ -910,8 +950,8 @@ cudaError_t rcm_launch_microbench(int which, double* out, const double* tab, lon
 }
 
 cudaError_t rcm_launch_cplkavg(int n, const double* lo, const double* hi, const double* t, double* out,
-                               cudaStream_t st) {
-    rcm_cplkavg_kernel<<<148, 256, 0, st>>>(n, lo, hi, t, out);
+                               const double* exp_tab, int narrow, cudaStream_t st) {
+    rcm_cplkavg_kernel<<<148, 256, 0, st>>>(n, lo, hi, t, out, exp_tab, narrow);
     return cudaGetLastError();
 }
 
@@ -920,10 +960,10 @@ size_t rcm_lbl_smem_bytes(int C, int nthreads) {
 }
 
 cudaError_t rcm_launch_lbl_step(const LblArgs& a, cudaStream_t st) {
-    constexpr int C = 32, NT = 192;
+    constexpr int C = RCM_LBL_C, NT = RCM_LBL_NT;
     rcm_lbl_prep_kernel<<<(a.ncol + 127) / 128, 128, 0, st>>>(a);
     const size_t smem = rcm_lbl_smem_bytes(C, NT);
-    auto kern = rcm_lbl_rt_kernel<C, NT>;
+    auto kern = a.clampk ? rcm_lbl_rt_kernel<C, NT, true> : rcm_lbl_rt_kernel<C, NT, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<a.ntiles * a.nchunks, NT, smem, st>>>(a);

@@ -11,6 +11,7 @@ constexpr int NLEV = RCM_NLEVEL;
 constexpr int MAX_ANGLE = 64;
 constexpr int MAX_TPERT = 16;
 constexpr int HALF = NLAY / 2;     // layers owned by each lane of a pair
+constexpr int RCM_LBL_C = 16, RCM_LBL_NT = 128;  // tile shape of the LBL radiative-transfer kernel
 constexpr int EXP_TAB = 64;        // entries of the 2^(j/64) table used by the solver's exp
 
 // Everything that is uniform over the ensemble.  Lives in __constant__ memory.
@@ -78,8 +79,9 @@ struct StepArgs {
 // Line-by-line path: arguments of the three per-step kernels.
 struct LblArgs {
     int ncol, ntiles, nwvl, nchunks, chunk_len, nact, h2o_slot, o3_slot;
+    int clampk;          // as StepArgs
     long step_index;
-    double co2_factor;
+    double co2_factor, tau_clamp;
     const double* __restrict__ wvl_lo;   // [nwvl] bin edges, nm
     const double* __restrict__ wvl_hi;
     const double* __restrict__ tau5;     // [5][nwvl][20]  H2O, CO2, O3, CH4, N2O
@@ -106,6 +108,6 @@ cudaError_t rcm_launch_microbench(int which, double* out, const double* tab, lon
 size_t rcm_lbl_smem_bytes(int C, int nthreads);
 cudaError_t rcm_launch_lbl_step(const LblArgs& a, cudaStream_t st);
 cudaError_t rcm_launch_cplkavg(int n, const double* lo, const double* hi, const double* t, double* out,
-                               cudaStream_t st);
+                               const double* exp_tab, int narrow, cudaStream_t st);
 
 #endif

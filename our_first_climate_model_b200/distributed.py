@@ -78,3 +78,22 @@ def global_means(scalars: torch.Tensor, ncol_total: int) -> dict:
     v = scalars.view(-1, 4)[-1]
     return {"toa_net_mean": float(v[0]) / ncol_total, "max_dT": float(v[1]),
             "converged_fraction": float(v[2]) / ncol_total, "max_abs_dE": float(v[3])}
+
+
+def run_to_equilibrium(solver, ncol_total: int, max_steps: int, check_every: int = 100) -> dict:
+    """The RCE driver loop over all ranks: every rank advances its own shard in blocks of `check_every` fused steps
+    (one launch per block, nothing crosses GPUs meanwhile); after each block ONE allreduce of the block's scalars
+    decides - identically on every rank - whether the whole ensemble is stationary (n_converged == ncol_total).
+    With one rank this is rcm_run_to_equilibrium."""
+    done = 0
+    means = None
+    while done < max_steps:
+        n = min(check_every, max_steps - done)
+        ptr = solver.advance_async(n)
+        sc = device_view(ptr, 4 * n)
+        allreduce_step_scalars(sc)
+        done += n
+        means = global_means(sc, ncol_total)  # .item() inside: waits for the block
+        if means["converged_fraction"] >= 1.0:
+            break
+    return {"steps": done, **(means or {})}

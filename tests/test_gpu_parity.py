@@ -130,6 +130,53 @@ def test_equilibrium_profile_within_1e_3_K(solver, rcm, golden):
     assert sc[-1, 1] < 1e-2  # stationarity diagnostic: the sorted profile has stopped moving
 
 
+def test_run_to_equilibrium_driver(solver, rcm, golden):
+    """The RCE driver loop: with an unreachable threshold it runs exactly max_steps (= the golden 6000-iteration
+    profile); with 1e-2 K per step it stops early with every column converged (the approach is slow: a few K away)."""
+    load(solver, rcm, golden, 100, slice(0, 1))
+    p = rcm.default_params()
+    p.solar_irr = float(golden["solar_irr"])
+    p.dT_converged = 0.0
+    solver.set_params(p)
+    done, last = solver.run_to_equilibrium(6000, 750)
+    st = solver.get_state()
+    assert done == 6000 and last[2] == 0
+    assert np.max(np.abs(st["Tlayer"] - golden["s6000_Tlayer_100"])) < 1e-3
+    p.dT_converged = 1e-2
+    solver.set_params(p)
+    load(solver, rcm, golden, 100, slice(0, 3))
+    done, last = solver.run_to_equilibrium(6000, 250)
+    assert done < 6000 and done % 250 == 0 and last[2] == 3 and last[1] < 1e-2
+    st = solver.get_state()
+    assert np.max(np.abs(st["Tlayer"][0] - golden["s6000_Tlayer_100"][0])) < 5.0
+    p.dT_converged = rcm.default_params().dT_converged
+    solver.set_params(p)
+
+
+def test_distributed_driver_single_rank_equals_c_driver(solver, rcm, golden):
+    """distributed.run_to_equilibrium (the N-rank loop; here one rank, no process group) == rcm_run_to_equilibrium."""
+    import torch
+    from our_first_climate_model_b200 import distributed as rdist
+    p = rcm.default_params()
+    p.solar_irr = float(golden["solar_irr"])
+    p.dT_converged = 5e-2
+    solver.set_params(p)
+    load(solver, rcm, golden, 20, slice(0, 5))
+    done_c, last_c = solver.run_to_equilibrium(3000, 200)
+    T_c = solver.get_state()["Tlayer"]
+    load(solver, rcm, golden, 20, slice(0, 5))
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        solver.set_stream(stream.cuda_stream)   # the scalars are read on the stream the solver launches on
+        res = rdist.run_to_equilibrium(solver, 5, 3000, 200)
+        stream.synchronize()
+        solver.set_stream(None)
+    assert res["steps"] == done_c and res["converged_fraction"] == 1.0 and res["max_dT"] == last_c[1]
+    assert np.array_equal(solver.get_state()["Tlayer"], T_c)
+    p.dT_converged = rcm.default_params().dT_converged
+    solver.set_params(p)
+
+
 def test_port_oracle_on_seeded_ensemble(solver, rcm, port, golden):
     """Seeded 200-column ensemble, one step, CUDA vs the plain-C oracle port."""
     atm = rcm.read_atm(table_path(100).replace("Reduced100Forcing.rcmtab", "column21.atm"))
@@ -202,6 +249,14 @@ def test_cplkavg_device_matches_reference(solver, golden_misc):
     m = golden_misc
     out = solver.cplkavg_device(m["cpl_lo"], m["cpl_hi"], m["cpl_T"])
     np.testing.assert_allclose(out, m["cpl_val"], rtol=1e-12)
+    # the LBL kernel's variant (solver exp / division in the narrow-band Simpson branch, generic code otherwise)
+    narrow = (1e7 / m["cpl_lo"] - 1e7 / m["cpl_hi"]) / (1e7 / m["cpl_lo"]) < 1e-2
+    assert narrow.any() and (~narrow).any()
+    solver.set_option(2, 1)
+    out2 = solver.cplkavg_device(m["cpl_lo"], m["cpl_hi"], m["cpl_T"])
+    solver.set_option(2, 0)
+    np.testing.assert_allclose(out2, m["cpl_val"], rtol=1e-12)
+    assert np.array_equal(out2[~narrow], out[~narrow])
 
 
 def test_kernels_really_ran(solver):
