@@ -41,7 +41,7 @@ struct rcm_solver {
     double *d_T = nullptr, *d_Ts = nullptr, *d_vmr = nullptr, *d_rh = nullptr, *d_Tprev = nullptr;
     float* d_time = nullptr;
     double *d_Ed = nullptr, *d_Eu = nullptr, *d_dE = nullptr, *d_dt = nullptr;
-    double *d_diag = nullptr, *d_scalars = nullptr, *d_tau = nullptr;
+    double *d_diag = nullptr, *d_scalars = nullptr, *d_tau = nullptr, *d_red = nullptr;
     int* d_lowpos = nullptr;
     size_t diag_steps = 0, tau_cap = 0;
     long step_index = 0;
@@ -253,6 +253,8 @@ int ensure_diag(rcm_solver* s, int nsteps) {
     if ((size_t)nsteps <= s->diag_steps && s->d_diag) return RCM_OK;
     CU(dalloc(s->d_diag, (size_t)nsteps * s->cap * 4));
     CU(dalloc(s->d_scalars, (size_t)nsteps * 4));
+    CU(dalloc(s->d_red, rcm_reduce_scratch_doubles(nsteps)));
+    CU(cudaMemsetAsync(s->d_red, 0, rcm_reduce_scratch_doubles(nsteps) * sizeof(double), s->stream));
     s->diag_steps = nsteps;
     return RCM_OK;
 }
@@ -431,7 +433,7 @@ int rcm_destroy(rcm_solver* s) {
     if (g_const_owner[s->device & 63] == s) g_const_owner[s->device & 63] = nullptr;
     void* ptrs[] = {s->d_xsec_file, s->d_coef, s->d_species, s->d_planck_c, s->d_planck_k, s->d_exp_tab, s->d_T, s->d_Ts, s->d_vmr, s->d_rh,
                     s->d_Tprev, s->d_time, s->d_lbl_lo, s->d_lbl_hi, s->d_lbl_tau5, s->d_lbl_h2o_ref, s->d_lbl_o3_ref, s->d_sH, s->d_sO,
-                    s->d_dTstat, s->d_part, s->d_Ed, s->d_Eu, s->d_dE, s->d_dt, s->d_diag, s->d_scalars, s->d_tau,
+                    s->d_dTstat, s->d_part, s->d_Ed, s->d_Eu, s->d_dE, s->d_dt, s->d_diag, s->d_scalars, s->d_red, s->d_tau,
                     s->d_lowpos};
     for (void* q : ptrs)
         if (q) cudaFree(q);
@@ -748,7 +750,7 @@ int rcm_advance_async(rcm_solver* s, int nsteps, double** d_scalars) {
     if (s->lbl_mode) {
         st = lbl_advance(s, nsteps);
         if (st != RCM_OK) return st;
-        CU(rcm_launch_reduce_diag(s->d_diag, nsteps, s->ncol, s->p.dT_converged, s->d_scalars, s->stream));
+        CU(rcm_launch_reduce_diag(s->d_diag, nsteps, s->ncol, s->p.dT_converged, s->d_red, s->d_scalars, s->stream));
         s->launches += 1;
         s->step_index += nsteps;
         if (d_scalars) *d_scalars = s->d_scalars;
@@ -756,7 +758,7 @@ int rcm_advance_async(rcm_solver* s, int nsteps, double** d_scalars) {
     }
     st = launch(s, MODE_STEP, nsteps, true);
     if (st != RCM_OK) return st;
-    CU(rcm_launch_reduce_diag(s->d_diag, nsteps, s->ncol, s->p.dT_converged, s->d_scalars, s->stream));
+    CU(rcm_launch_reduce_diag(s->d_diag, nsteps, s->ncol, s->p.dT_converged, s->d_red, s->d_scalars, s->stream));
     s->launches += 1;
     s->step_index += nsteps;
     s->tau_valid = false;
@@ -874,7 +876,7 @@ int rcm_step_host(rcm_solver* s, const double* Tlayer_in, const double* Tsurf_in
         CU(cudaEventRecord(s->pipe_done[i], s->pipe_stream[i]));
         CU(cudaStreamWaitEvent(s->stream, s->pipe_done[i], 0));
     }
-    CU(rcm_launch_reduce_diag(s->d_diag, 1, s->ncol, s->p.dT_converged, s->d_scalars, s->stream));
+    CU(rcm_launch_reduce_diag(s->d_diag, 1, s->ncol, s->p.dT_converged, s->d_red, s->d_scalars, s->stream));
     s->launches += 1;
     s->step_index += 1;
     s->tau_valid = false;

@@ -536,23 +536,14 @@ __global__ void rcm_coef_kernel(const double* __restrict__ src, double* __restri
 }
 
 // ------------------------------------------------------------------------------------------
-// Per-step ensemble scalars from the per-column diagnostics: one CTA per step, fixed-order
-// tree so the result does not depend on scheduling.  out[step] = {sum toa, max dT, #converged,
-// max|dE|} (layout of rcm_step_scalars).
+// Per-step ensemble scalars from the per-column diagnostics.  RED_BLOCKS CTAs per step reduce fixed slices
+// of the columns with a fixed-order tree into partial[step][block][4]; the CTA that finishes last (ticket
+// counter, reset for the next launch) folds the partials in block order.  The result does not depend on
+// scheduling.  out[step] = {sum toa, max dT, #converged, max|dE|} (layout of rcm_step_scalars).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) rcm_reduce_diag_kernel(const double* __restrict__ diag, int ncol,
-                                                               double dT_conv, double* __restrict__ out) {
-    __shared__ double sh[4][32];
-    const int step = blockIdx.x;
-    const double* d = diag + (size_t)step * ncol * 4;
-    double sum = 0.0, mx = 0.0, cnt = 0.0, mde = 0.0;
-    for (int i = threadIdx.x; i < ncol; i += blockDim.x) {
-        const double4 v = *reinterpret_cast<const double4*>(d + (size_t)i * 4);
-        sum += v.x;
-        mx = fmax(mx, v.y);
-        cnt += (v.y < dT_conv) ? 1.0 : 0.0;
-        mde = fmax(mde, v.z);
-    }
+constexpr int RED_BLOCKS = 64, RED_THREADS = 256;
+
+__device__ __forceinline__ void red4(double& sum, double& mx, double& cnt, double& mde, double (*sh)[RED_THREADS / 32]) {
     for (int o = 16; o > 0; o >>= 1) {
         sum += __shfl_xor_sync(0xffffffffu, sum, o);
         mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -560,24 +551,69 @@ __global__ void __launch_bounds__(1024) rcm_reduce_diag_kernel(const double* __r
         mde = fmax(mde, __shfl_xor_sync(0xffffffffu, mde, o));
     }
     const int w = threadIdx.x >> 5, ln = threadIdx.x & 31;
+    __syncthreads();
     if (ln == 0) {
         sh[0][w] = sum; sh[1][w] = mx; sh[2][w] = cnt; sh[3][w] = mde;
     }
     __syncthreads();
-    if (w == 0) {
-        const int nw = blockDim.x >> 5;
-        sum = ln < nw ? sh[0][ln] : 0.0;
-        mx = ln < nw ? sh[1][ln] : 0.0;
-        cnt = ln < nw ? sh[2][ln] : 0.0;
-        mde = ln < nw ? sh[3][ln] : 0.0;
+    constexpr int NW = RED_THREADS / 32;
+    sum = ln < NW ? sh[0][ln] : 0.0;
+    mx = ln < NW ? sh[1][ln] : 0.0;
+    cnt = ln < NW ? sh[2][ln] : 0.0;
+    mde = ln < NW ? sh[3][ln] : 0.0;
+    for (int o = NW / 2; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        mde = fmax(mde, __shfl_xor_sync(0xffffffffu, mde, o));
+    }
+}
+
+__global__ void __launch_bounds__(RED_THREADS) rcm_reduce_diag_kernel(const double* __restrict__ diag, int ncol,
+                                                                      double dT_conv, double* __restrict__ partial,
+                                                                      unsigned* __restrict__ ticket,
+                                                                      double* __restrict__ out) {
+    __shared__ double sh[4][RED_THREADS / 32];
+    __shared__ bool last;
+    const int step = blockIdx.y, b = blockIdx.x;
+    const double* d = diag + (size_t)step * ncol * 4;
+    const int per = (ncol + RED_BLOCKS - 1) / RED_BLOCKS, lo = b * per, hi = min(ncol, lo + per);
+    double sum = 0.0, mx = 0.0, cnt = 0.0, mde = 0.0;
+    for (int i = lo + threadIdx.x; i < hi; i += RED_THREADS) {
+        const double4 v = *reinterpret_cast<const double4*>(d + (size_t)i * 4);
+        sum += v.x;
+        mx = fmax(mx, v.y);
+        cnt += (v.y < dT_conv) ? 1.0 : 0.0;
+        mde = fmax(mde, v.z);
+    }
+    red4(sum, mx, cnt, mde, sh);
+    if (threadIdx.x == 0) {
+        double* pp = partial + ((size_t)step * RED_BLOCKS + b) * 4;
+        pp[0] = sum; pp[1] = mx; pp[2] = cnt; pp[3] = mde;
+        __threadfence();
+        last = (atomicAdd(ticket + step, 1u) == RED_BLOCKS - 1);
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    sum = mx = cnt = mde = 0.0;
+    if (threadIdx.x < 32) {  // 64 partials, two per lane, folded in block order by the fixed tree
+        for (int k = threadIdx.x; k < RED_BLOCKS; k += 32) {
+            const double* pp = partial + ((size_t)step * RED_BLOCKS + k) * 4;
+            sum += pp[0];
+            mx = fmax(mx, pp[1]);
+            cnt += pp[2];
+            mde = fmax(mde, pp[3]);
+        }
         for (int o = 16; o > 0; o >>= 1) {
             sum += __shfl_xor_sync(0xffffffffu, sum, o);
             mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
             cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
             mde = fmax(mde, __shfl_xor_sync(0xffffffffu, mde, o));
         }
-        if (ln == 0) {
+        if (threadIdx.x == 0) {
             out[step * 4 + 0] = sum; out[step * 4 + 1] = mx; out[step * 4 + 2] = cnt; out[step * 4 + 3] = mde;
+            ticket[step] = 0;
         }
     }
 }
@@ -925,9 +961,13 @@ cudaError_t rcm_launch_step(int mode, const StepArgs& a, int nactive, int grid, 
     return cudaErrorInvalidValue;
 }
 
-cudaError_t rcm_launch_reduce_diag(const double* diag, int nsteps, int ncol, double dT_converged, double* scalars,
-                                   cudaStream_t st) {
-    rcm_reduce_diag_kernel<<<nsteps, 1024, 0, st>>>(diag, ncol, dT_converged, scalars);
+size_t rcm_reduce_scratch_doubles(int nsteps) { return (size_t)nsteps * (RED_BLOCKS * 4 + 1); }
+
+// scratch: rcm_reduce_scratch_doubles(nsteps) doubles, zeroed once when allocated (the tickets live at its end)
+cudaError_t rcm_launch_reduce_diag(const double* diag, int nsteps, int ncol, double dT_converged, double* scratch,
+                                   double* scalars, cudaStream_t st) {
+    unsigned* ticket = reinterpret_cast<unsigned*>(scratch + (size_t)nsteps * RED_BLOCKS * 4);
+    rcm_reduce_diag_kernel<<<dim3(RED_BLOCKS, nsteps), RED_THREADS, 0, st>>>(diag, ncol, dT_converged, scratch, ticket, scalars);
     return cudaGetLastError();
 }
 

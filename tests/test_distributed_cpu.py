@@ -37,6 +37,13 @@ def _worker(rank, world, port, out):
     full = np.stack([diag[:, :, 0].sum(1), np.abs(diag[:, :, 1]).max(1), (np.abs(diag[:, :, 1]) < 0.5).sum(1),
                      np.abs(diag[:, :, 2]).max(1)], axis=1)
     ok = np.allclose(t.numpy(), full, rtol=1e-12, atol=1e-12)
+    # the asynchronous per-step exchange: same numbers, several steps in flight, ring reuse
+    ex = rdist.StepScalarExchange(torch.device("cpu"), ring=2)
+    tickets = [ex.submit(torch.from_numpy(sc[k].copy())) for k in range(3)]
+    ok = ok and np.allclose(ex.result(tickets[2]).numpy(), full[2], rtol=1e-12, atol=1e-12)
+    ok = ok and np.allclose(ex.result(tickets[1]).numpy(), full[1], rtol=1e-12, atol=1e-12)
+    ok = ok and np.allclose(ex.latest().numpy(), full[2], rtol=1e-12, atol=1e-12)
+    ex.drain()
     mx = rdist.max_over_ranks(10.0 + rank)
     means = rdist.global_means(t, ncol)
     rdist.barrier()
