@@ -144,9 +144,12 @@ def radiative_transfer(tau, wvl, weight, Tlayer, T_surface, solar_irr):
 
 
 def advance(tab, plevel, rel_hum, solar_irr, Tlayer, Tsurf, vmr9, nsteps, first_step=0, cloud_on=True,
-            time_h=None, want_trace=False, tau_s=2.0):
+            time_h=None, want_trace=False, tau_s=2.0, **overrides):
+    """overrides: fields of Params (nangle, cloud_layer, max_dT, dt_cap, ...) away from the reference's Consts."""
     t = ctable(tab)
     p = default_params(solar_irr, cloud_on, tau_s)
+    for k, v in overrides.items():
+        setattr(p, k, v)
     Tl = np.array(Tlayer, dtype=np.float64, order="C").reshape(-1, NLAY)
     ncol = Tl.shape[0]
     Ts = np.array(np.broadcast_to(Tsurf, (ncol,)), dtype=np.float64, order="C")

@@ -24,6 +24,7 @@ struct rcm_solver {
     int opt_angle_cubes = 1;
     int opt_config = 0;        // 0: planned (plan_parts); k > 0: force kShapes[k-1] for the whole ensemble
         // prepare the next wavelength inside the angle loop (0: separate phase)
+    int opt_stage_rows = 1;    // K1 reads its table rows from shared memory, staged one wavelength ahead
     int opt_cplk_narrow = 0;   // rcm_cplkavg_device evaluates the LBL kernel's narrow-band variant (tests)
     double tau_clamp = 240.0;  // set by build_angles
     int clampk = 1;
@@ -318,6 +319,7 @@ int launch_part(rcm_solver* s, int mode, int nsteps, bool want_diag, const Part&
     a.ntiles = (p.ncols + a.C - 1) / a.C;
     a.nthreads = p.sh.nthreads;
     a.clampk = s->clampk;
+    a.stage_rows = s->opt_stage_rows;
     a.tau_clamp = s->tau_clamp;
     a.nsteps = nsteps;
     a.step_index = s->step_index;
@@ -478,6 +480,10 @@ int rcm_set_option(rcm_solver* s, int option, int value) {
     }
     if (option == 2) {
         s->opt_cplk_narrow = value ? 1 : 0;
+        return RCM_OK;
+    }
+    if (option == 3) {
+        s->opt_stage_rows = value ? 1 : 0;
         return RCM_OK;
     }
     return fail(s, RCM_ERR_ARG, "unknown option");

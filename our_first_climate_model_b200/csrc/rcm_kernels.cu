@@ -51,9 +51,9 @@ __device__ __forceinline__ double exp_scaled(double a, double b_l2e64, unsigned 
     const double f = fma(a, b_l2e64, -kd);  // exact product minus an integer: one rounding
     if (CLAMPK) k = max(k, -64000);
     double Ts;  // tab_lane: shared-window byte address of this lane's copy of entry 0 (entries are 256 B apart)
-    asm("{\n\t.reg .b32 j, ad;\n\tand.b32 j, %1, 63;\n\tmad.lo.u32 ad, j, 256, %2;\n\tld.shared.f64 %0, [ad];\n\t}"
+    asm("{\n\t.reg .b32 j, ad;\n\tand.b32 j, %1, 63;\n\tmad.lo.u32 ad, j, %3, %2;\n\tld.shared.f64 %0, [ad];\n\t}"
         : "=d"(Ts)
-        : "r"(k), "r"(tab_lane));
+        : "r"(k), "r"(tab_lane), "n"(EXP_REP * 8));
     const double T = __hiloint2double(__double2hiint(Ts) + (k << 14), __double2loint(Ts));  // 2^(k/64)
     // Horner coefficients c^5/120, c^4/24, c^3/6, c^2/2, c (c = ln2/64) come from the constant bank: as
     // literals each block of ten exp's would re-materialise them into uniform registers (10 UMOV per block)
@@ -191,9 +191,30 @@ __device__ __forceinline__ void sweep_item(const double (&tau)[HALF], const doub
 // arrays are stored in this order: row(l) = l for l<10, 29-l otherwise (= 10*h + j).
 __device__ __forceinline__ constexpr int prow(int l) { return l < HALF ? l : 29 - l; }
 
-template <int C, int NT>
+constexpr int ROWB = 5 * 32;             // bytes of one table row: 5 active species x {c0, cT, cP, cPT}
+constexpr int NCAND = 3;                 // candidate rows per layer: temperature intervals it_min .. it_min + 2 of the tile
+constexpr int ROWBUF = NLAY * NCAND * ROWB;  // per warp: 60 rows, 9600 bytes
+
+// 16-byte asynchronous global -> shared copies (LDGSTS) for the row staging.  (cp.async.bulk was tried first: its
+// operands live in uniform registers, so 40 per-lane row copies became a 40-trip ELECT/R2UR/UBLKCP waterfall.)
+__device__ __forceinline__ void cp_async16(unsigned dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// STAGE (16-column tiles, the five default species): every warp owns a 9600-byte buffer that receives, by
+// cp.async while the previous wavelength's angles run, the table rows its next wavelength needs; after the
+// wavelength loop the first 5376 bytes carry the warp's flux partials into the spectral reduction and the tails of
+// the first three buffers hold the tile's reduced fluxes (Ed, Eu, dE).
+template <int C, int NT, int NACT>
 struct Smem {
-    double* exp_tab;  // [64][32]
+    static constexpr bool STAGE = (C == 16 && NACT == 5);
+    static constexpr int G = NT / (2 * C), NW = NT / 32;
+    static constexpr size_t PART = 2 * (size_t)NLEV * C;  // doubles of one wavelength group's partial fluxes [42][C]
+    static constexpr size_t EP_BYTES = STAGE ? (size_t)NW * ROWBUF : (size_t)G * PART * sizeof(double);
+    static_assert(!STAGE || (G == NW && NW >= 3 && (PART + NLEV * C) * sizeof(double) <= (size_t)ROWBUF), "one warp per wavelength group");
+    double* exp_tab;  // [64][16]
     double* T;        // [20][C] layer temperature (sorted), rows in pair order
     double* invT;     // [20][C]
     double* delT;     // [20][C]
@@ -201,19 +222,25 @@ struct Smem {
     double* Ts;       // [C]
     double* invTs;    // [C]
     double* dt;       // [C]
-    int* it;          // [20][C]
-    double* Ep;       // [21][NT/2] reduction staging
     double* Ed;       // [21][C]   natural level order
     double* Eu;       // [21][C]
     double* dE;       // [20][C]   natural layer order
-    static constexpr size_t REGION = (size_t)NLEV * (NT / 2) + 2 * (size_t)NLEV * C + (size_t)NLAY * C;
+    unsigned char* ep;  // partial fluxes of group gg at ep + gg * ep_stride (STAGE: = that warp's row buffer)
+    int* it;          // [20][C]
+    int* rowsel;      // [20][C] byte offset of the (layer, column)'s row inside the warp's row buffer
+    int* rowoff;      // [20][NCAND] first row (cell * nwvl) of the candidates of every layer (pair order)
+    int* itmin;       // [20]
+    int* outside;     // [20] then [10]: some column of the tile needs a row beyond the two candidates
+    static constexpr size_t ep_stride = STAGE ? (size_t)ROWBUF : PART * sizeof(double);
     static size_t bytes(int nactive) {
-        return ((size_t)EXP_TAB * 32 + 3 * (size_t)NLAY * C + (size_t)nactive * NLAY * C + 3 * (size_t)C +
-                REGION) * sizeof(double) + (size_t)NLAY * C * sizeof(int);
+        return ((size_t)EXP_TAB * EXP_REP + 3 * (size_t)NLAY * C + (size_t)nactive * NLAY * C + 3 * (size_t)C +
+                (STAGE ? 0 : 2 * (size_t)NLEV * C + (size_t)NLAY * C)) * sizeof(double) + EP_BYTES +
+               (2 * (size_t)NLAY * C + (NCAND + 3) * NLAY + HALF + 2) * sizeof(int);
     }
     __device__ __forceinline__ Smem(unsigned char* base, int nactive) {
         double* p = reinterpret_cast<double*>(base);
-        exp_tab = p; p += EXP_TAB * 32;
+        exp_tab = p; p += EXP_TAB * EXP_REP;
+        ep = reinterpret_cast<unsigned char*>(p); p += EP_BYTES / sizeof(double);  // 128-byte aligned: 8 KB into the block
         T = p;       p += NLAY * C;
         invT = p;    p += NLAY * C;
         delT = p;    p += NLAY * C;
@@ -221,19 +248,27 @@ struct Smem {
         Ts = p;      p += C;
         invTs = p;   p += C;
         dt = p;      p += C;
-        Ep = p;
-        Ed = Ep + NLEV * (NT / 2);
-        Eu = Ed + NLEV * C;
-        dE = Eu + NLEV * C;
-        p += REGION;
+        if (STAGE) {  // tails of the row buffers (free while the partials are reduced and until the next request)
+            Ed = reinterpret_cast<double*>(ep + 0 * ep_stride) + PART;
+            Eu = reinterpret_cast<double*>(ep + 1 * ep_stride) + PART;
+            dE = reinterpret_cast<double*>(ep + 2 * ep_stride) + PART;
+        } else {
+            Ed = p;      p += NLEV * C;
+            Eu = p;      p += NLEV * C;
+            dE = p;      p += NLAY * C;
+        }
         it = reinterpret_cast<int*>(p);
+        rowsel = it + NLAY * C;
+        rowoff = rowsel + NLAY * C;
+        itmin = rowoff + NCAND * NLAY;
+        outside = itmin + NLAY;
     }
 };
 
 // Table indices and interpolation weights in T for every (layer, column) of the tile, from the
 // temperatures currently in s.T (repwvl_thermal.cpp:229-239).
-template <int C, int NT>
-__device__ __forceinline__ void prep_tau_indices(const Smem<C, NT>& s, int tid) {
+template <int C, int NT, int NACT>
+__device__ __forceinline__ void prep_tau_indices(const Smem<C, NT, NACT>& s, int tid) {
     for (int i = tid; i < NLAY * C; i += NT) {
         const int r = i / C;  // pair-order row; tref_ip is stored in the same order
         const double midT = s.T[i];
@@ -249,17 +284,40 @@ constexpr int min_ctas(int NT) { return (NT == 256 || NT == 512) ? 512 / NT : 38
 
 template <int MODE, int NACT, int C, int NT, bool CLAMPK>
 __global__ void __launch_bounds__(NT, min_ctas(NT)) rcm_step_kernel(const StepArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int G = NT / (2 * C);  // wavelength groups
     const int tid = threadIdx.x, lane = tid & 31;
     const int h = tid & 1, q = tid >> 1, c = q % C, g = q / C;
     const int nact = (NACT > 0) ? NACT : cst.nactive;
-    const Smem<C, NT> s(smem_raw, nact);
+    using SM = Smem<C, NT, NACT>;
+    const SM s(smem_raw, nact);
     const int sb = h * HALF * C + c;  // this thread's row block in the per-layer arrays
 
-    for (int i = tid; i < EXP_TAB * 32; i += NT) s.exp_tab[i] = a.exp_tab[i >> 5];
-    const unsigned tab_lane = (unsigned)__cvta_generic_to_shared(s.exp_tab + lane);
+    for (int i = tid; i < EXP_TAB * EXP_REP; i += NT) s.exp_tab[i] = a.exp_tab[i / EXP_REP];
+    const unsigned tab_lane = (unsigned)__cvta_generic_to_shared(s.exp_tab + (lane & (EXP_REP - 1)));
     const int nwvl = cst.nwvl;
+    // row staging (STAGE): this warp's buffer
+    const bool stage = SM::STAGE && MODE == MODE_STEP && a.stage_rows;
+    const int warp = tid >> 5;
+    unsigned char* const rows = s.ep + (size_t)warp * SM::ep_stride;
+    const unsigned rows_addr = (unsigned)__cvta_generic_to_shared(rows);
+    // Start the copies of the 60 rows of wavelength w (three candidates per layer, 160 bytes each): lane q copies
+    // rows q and q + 32 in 16-byte pieces.  The buffer must be free: all lanes have consumed the previous fill.
+    auto request_rows = [&](int w) {
+        __syncwarp();
+        const char* base = reinterpret_cast<const char*>(a.coef) + (size_t)w * ROWB;
+        for (int row = lane; row < NCAND * NLAY; row += 32) {
+            const char* src = base + (size_t)s.rowoff[row] * ROWB;
+            const unsigned dst = rows_addr + row * ROWB;
+#pragma unroll
+            for (int part = 0; part < ROWB / 16; ++part) cp_async16(dst + part * 16, src + part * 16);
+        }
+        cp_async_commit();
+    };
+    auto wait_rows = [&] {
+        cp_async_wait_all();
+        __syncwarp();
+    };
 
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
         const int col0 = tile * C;
@@ -269,7 +327,7 @@ __global__ void __launch_bounds__(NT, min_ctas(NT)) rcm_step_kernel(const StepAr
         // ---- load the tile's state: T [20][C], surface T, active VMRs -----------------------
         for (int i = tid; i < NLAY * C; i += NT) {
             const int l = i / C, cc = i % C;
-            s.T[prow(l) * C + cc] = (cc < ncl) ? a.Tlayer[(size_t)(col0 + cc) * NLAY + l] : 250.0;
+            s.T[prow(l) * C + cc] = a.Tlayer[(size_t)(col0 + (cc < ncl ? cc : 0)) * NLAY + l];  // padding = column 0
         }
         for (int i = tid; i < nact * NLAY * C; i += NT) {
             const int cc = i % C, l = (i / C) % NLAY, sp = i / (C * NLAY);
@@ -283,17 +341,15 @@ __global__ void __launch_bounds__(NT, min_ctas(NT)) rcm_step_kernel(const StepAr
         // sections in the reference's operation order, no FMA contraction -> tau is bit-identical to
         // read_tau's for identical inputs.  The four bilinear coefficients c0, cT, cP, cPT
         // (repwvl_thermal.cpp:235-238) depend on the table alone and are precomputed per cell (rcm_coef_kernel).
-        auto tau_cell = [&](int j, int w) -> double {
+        auto tau_from = [&](int j, const double2* cf) -> double {
             const int r = h * HALF + j;
             const double dT = s.delT[sb + j * C], dP = cst.delP[r];
-            const int cell = cst.ipcell[r] + s.it[sb + j * C];
-            const double2* cf = reinterpret_cast<const double2*>(a.coef) + (size_t)(cell * nwvl + w) * 2 * nact;
             double acc = 0.0;
 #pragma unroll
             for (int k = 0; k < (NACT > 0 ? NACT : RCM_NSPECIES); ++k) {
                 if (NACT == 0 && k >= nact) break;
                 // two 128-bit loads (one 256-bit LDG.E.ENL2.256 was measured 8% slower for the whole step)
-                const double2 c0T = __ldg(cf + 2 * k), cPPT = __ldg(cf + 2 * k + 1);
+                const double2 c0T = cf[2 * k], cPPT = cf[2 * k + 1];
                 double v = __dadd_rn(c0T.x, __dmul_rn(c0T.y, dT));
                 v = __dadd_rn(v, __dmul_rn(cPPT.x, dP));
                 v = __dadd_rn(v, __dmul_rn(__dmul_rn(cPPT.y, dT), dP));
@@ -302,6 +358,15 @@ __global__ void __launch_bounds__(NT, min_ctas(NT)) rcm_step_kernel(const StepAr
             acc = __dmul_rn(acc, cst.numDens[r]);
             if (cst.cloud_row == r) acc = __dadd_rn(acc, cst.cloud_tau);  // main.cpp:270
             return acc;
+        };
+        // ... with the coefficients read from the table in global memory
+        auto tau_cell = [&](int j, int w) -> double {
+            const int cell = cst.ipcell[h * HALF + j] + s.it[sb + j * C];
+            return tau_from(j, reinterpret_cast<const double2*>(a.coef) + (size_t)(cell * nwvl + w) * 2 * nact);
+        };
+        // ... or from the rows staged in this warp's buffer
+        auto tau_staged = [&](int j) -> double {
+            return tau_from(j, reinterpret_cast<const double2*>(rows + s.rowsel[sb + j * C]));
         };
         // tau of owned layer j at wavelength w as the transmissions will use it (w is clamped by the caller)
         auto tau_use = [&](int j, int w) -> double {
@@ -369,6 +434,31 @@ __global__ void __launch_bounds__(NT, min_ctas(NT)) rcm_step_kernel(const StepAr
             for (int i = tid; i < NLAY * C; i += NT) s.invT[i] = 1.0 / s.T[i];
             if (tid < C) s.invTs[tid] = 1.0 / s.Ts[tid];
             __syncthreads();
+            if (stage) {
+                // the candidate rows of every layer: temperature intervals it_min .. it_min + 2 of the tile's columns
+                if (tid < NLAY) {
+                    int mn = s.it[tid * C], mx = mn;
+                    for (int cc = 1; cc < C; ++cc) {
+                        mn = min(mn, s.it[tid * C + cc]);
+                        mx = max(mx, s.it[tid * C + cc]);
+                    }
+                    s.itmin[tid] = mn;
+                    s.outside[tid] = (mx - mn >= NCAND);
+                    for (int k = 0; k < NCAND; ++k)
+                        s.rowoff[NCAND * tid + k] = (cst.ipcell[tid] + min(mn + k, cst.n_tpert - 2)) * nwvl;
+                }
+                __syncthreads();
+                for (int i = tid; i < NLAY * C; i += NT) {
+                    const int r = i / C;
+                    s.rowsel[i] = (NCAND * r + min(s.it[i] - s.itmin[r], NCAND - 1)) * ROWB;
+                }
+                if (tid == 0) {
+                    int any = 0;
+                    for (int r = 0; r < NLAY; ++r) any |= s.outside[r];
+                    s.outside[NLAY] = any;
+                }
+                __syncthreads();
+            }
 
             if (MODE == MODE_TAU) {  // K1 alone: the compute part of read_tau + cloud_into_tau
                 if (a.lowpos_t) {
@@ -399,14 +489,29 @@ __global__ void __launch_bounds__(NT, min_ctas(NT)) rcm_step_kernel(const StepAr
             // provably warp-uniform: a thread whose last item does not exist (w >= nwvl) repeats the last
             // wavelength with a zero Planck factor, which adds exactly 0 to every flux.
             const int nitem = (nwvl + G - 1) / G;
+            if (stage) request_rows(min(g, nwvl - 1));
 #pragma unroll 1
             for (int item = 0; item < nitem; ++item) {
                 const int w_any = g + item * G;
                 const bool real = w_any < nwvl;
                 const int w = real ? w_any : nwvl - 1;
                 double tau[HALF], Bo[HALF];
+                if (stage) wait_rows();  // the rows of this wavelength were requested one wavelength ago
+                // two straight-line versions of K1 (a branch per layer would cut the block the loads are scheduled in);
+                // a tile where some column needs a row beyond the two candidates takes the global one for every layer
+                if (stage && !s.outside[NLAY]) {
 #pragma unroll
-                for (int j = 0; j < HALF; ++j) tau[j] = tau_use(j, w);
+                    for (int j = 0; j < HALF; ++j) {
+                        const double v = tau_staged(j);
+                        tau[j] = CLAMPK ? v : fmin(v, a.tau_clamp);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < HALF; ++j) tau[j] = tau_use(j, w);
+                }
+                // K1 has consumed the buffer: the rows of the NEXT wavelength travel while this one's angles run
+                // (nothing is requested after the last one: the buffer then carries the flux partials)
+                if (stage && item + 1 < nitem) request_rows(min(w_any + G, nwvl - 1));
                 // K2: Planck source B = k_w / (exp(c_w / T) - 1) (main.cpp:188-191 regrouped so that everything
                 // that depends on the wavelength alone is precomputed on the host); surface: main.cpp:301
                 const double pc = __ldg(a.planck_c + w), pk = real ? __ldg(a.planck_k + w) : 0.0;
@@ -418,29 +523,28 @@ __global__ void __launch_bounds__(NT, min_ctas(NT)) rcm_step_kernel(const StepAr
             }
 
             // ---------------- K4: reduce the G wavelength groups of every column ---------------
-            constexpr int GC = G * C;
-            // E_down, levels 1..20 (staging row = level-1)
+            // every group leaves its partial fluxes in its own buffer [42][C] (row l: E_down[l+1] for l < 20, row 21+l:
+            // E_up[l]); the groups are then summed in a fixed order
+            {
+                double* part = reinterpret_cast<double*>(s.ep + (size_t)g * SM::ep_stride);
 #pragma unroll
-            for (int j = 0; j < HALF; ++j) s.Ep[(h ? (NLAY - 1 - j) : j) * GC + g * C + c] = h ? E2[j] : E1[j];
-            __syncthreads();
-            for (int i = tid; i < NLAY * C; i += NT) {
-                const int l = i / C, cc = i % C;
-                double sum = 0.0;
-                for (int gg = 0; gg < G; ++gg) sum += s.Ep[l * GC + gg * C + cc];
-                s.Ed[(l + 1) * C + cc] = sum;
+                for (int j = 0; j < HALF; ++j) {
+                    const int l = h ? (NLAY - 1 - j) : j;
+                    part[l * C + c] = h ? E2[j] : E1[j];
+                    part[(NLEV + l) * C + c] = h ? E1[j] : E2[j];
+                }
+                if (h) part[(NLEV + NLAY) * C + c] = Eu20;
             }
-            if (tid < C) s.Ed[tid] = 0.0;  // E_down at the top of the atmosphere stays 0 (main.cpp:300)
             __syncthreads();
-            // E_up, levels 0..20
-#pragma unroll
-            for (int j = 0; j < HALF; ++j) s.Ep[(h ? (NLAY - 1 - j) : j) * GC + g * C + c] = h ? E1[j] : E2[j];
-            if (h) s.Ep[NLAY * GC + g * C + c] = Eu20;
-            __syncthreads();
-            for (int i = tid; i < NLEV * C; i += NT) {
-                const int l = i / C, cc = i % C;
+            for (int i = tid; i < 2 * NLEV * C; i += NT) {
+                const int row = i / C;
+                if (row == NLAY) {
+                    s.Ed[i % C] = 0.0;  // E_down at the top of the atmosphere stays 0 (main.cpp:300)
+                    continue;
+                }
                 double sum = 0.0;
-                for (int gg = 0; gg < G; ++gg) sum += s.Ep[l * GC + gg * C + cc];
-                s.Eu[i] = sum;
+                for (int gg = 0; gg < G; ++gg) sum += reinterpret_cast<const double*>(s.ep + (size_t)gg * SM::ep_stride)[i];
+                if (row < NLAY) s.Ed[i + C] = sum; else s.Eu[i - NLEV * C] = sum;
             }
             __syncthreads();
             // heating rates (main.cpp:337-341)
@@ -624,10 +728,10 @@ __global__ void __launch_bounds__(RED_THREADS) rcm_reduce_diag_kernel(const doub
 // ------------------------------------------------------------------------------------------
 template <int WHICH>
 __global__ void __launch_bounds__(256) rcm_microbench_kernel(double* out, long iters, const double* tab) {
-    __shared__ double stab[EXP_TAB * 32];
-    for (int i = threadIdx.x; i < EXP_TAB * 32; i += blockDim.x) stab[i] = tab[i >> 5];
+    __shared__ double stab[EXP_TAB * EXP_REP];
+    for (int i = threadIdx.x; i < EXP_TAB * EXP_REP; i += blockDim.x) stab[i] = tab[i / EXP_REP];
     __syncthreads();
-    const unsigned tl = (unsigned)__cvta_generic_to_shared(stab + (threadIdx.x & 31));
+    const unsigned tl = (unsigned)__cvta_generic_to_shared(stab + (threadIdx.x & (EXP_REP - 1)));
     double v[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) v[k] = -1.0 - 0.001 * (threadIdx.x + k);
@@ -772,10 +876,10 @@ __global__ void __launch_bounds__(128) rcm_lbl_prep_kernel(const LblArgs a) {
 
 template <int C, int NT, bool CLAMPK>
 __global__ void __launch_bounds__(NT, 384 / NT) rcm_lbl_rt_kernel(const LblArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int G = NT / (2 * C), GC = G * C;
     double* p = reinterpret_cast<double*>(smem_raw);
-    double* s_tab = p; p += EXP_TAB * 32;
+    double* s_tab = p; p += EXP_TAB * EXP_REP;
     double* s_T = p;   p += NLAY * C;
     double* s_sH = p;  p += NLAY * C;
     double* s_sO = p;  p += NLAY * C;
@@ -784,8 +888,8 @@ __global__ void __launch_bounds__(NT, 384 / NT) rcm_lbl_rt_kernel(const LblArgs 
     const int tid = threadIdx.x, lane = tid & 31;
     const int h = tid & 1, q = tid >> 1, c = q % C, g = q / C;
     const int sb = h * HALF * C + c;
-    for (int i = tid; i < EXP_TAB * 32; i += NT) s_tab[i] = a.exp_tab[i >> 5];
-    const unsigned tab_lane = (unsigned)__cvta_generic_to_shared(s_tab + lane);
+    for (int i = tid; i < EXP_TAB * EXP_REP; i += NT) s_tab[i] = a.exp_tab[i / EXP_REP];
+    const unsigned tab_lane = (unsigned)__cvta_generic_to_shared(s_tab + (lane & (EXP_REP - 1)));
     const int tile = blockIdx.x % a.ntiles, chunk = blockIdx.x / a.ntiles;
     const int col0 = tile * C, ncl = min(C, a.ncol - col0);
     for (int i = tid; i < NLAY * C; i += NT) {
@@ -908,10 +1012,10 @@ __global__ void __launch_bounds__(128) rcm_lbl_finish_kernel(const LblArgs a) {
 
 __global__ void __launch_bounds__(256) rcm_cplkavg_kernel(int n, const double* lo, const double* hi, const double* t,
                                                           double* out, const double* tab, int narrow) {
-    __shared__ double stab[EXP_TAB * 32];
-    for (int i = threadIdx.x; i < EXP_TAB * 32; i += blockDim.x) stab[i] = tab[i >> 5];
+    __shared__ double stab[EXP_TAB * EXP_REP];
+    for (int i = threadIdx.x; i < EXP_TAB * EXP_REP; i += blockDim.x) stab[i] = tab[i / EXP_REP];
     __syncthreads();
-    const unsigned tl = (unsigned)__cvta_generic_to_shared(stab + (threadIdx.x & 31));
+    const unsigned tl = (unsigned)__cvta_generic_to_shared(stab + (threadIdx.x & (EXP_REP - 1)));
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
         out[i] = narrow ? cplkavg_narrow(lo[i], hi[i], 1.0E7 / lo[i], 1.0E7 / hi[i], t[i], tl) : cplkavg_dev(lo[i], hi[i], t[i]);
 }
@@ -919,17 +1023,20 @@ __global__ void __launch_bounds__(256) rcm_cplkavg_kernel(int n, const double* l
 }  // namespace
 
 size_t rcm_step_smem_bytes(int C, int nactive, int nthreads) {
-    if (C == 16 && nthreads == 128) return Smem<16, 128>::bytes(nactive);
-    if (C == 8 && nthreads == 128) return Smem<8, 128>::bytes(nactive);
-    if (C == 4 && nthreads == 128) return Smem<4, 128>::bytes(nactive);
-    if (C == 32 && nthreads == 192) return Smem<32, 192>::bytes(nactive);
-    if (C == 16 && nthreads == 96) return Smem<16, 96>::bytes(nactive);
+#define RCM_SHAPE(CC, TT) \
+    if (C == CC && nthreads == TT) return nactive == 5 ? Smem<CC, TT, 5>::bytes(5) : Smem<CC, TT, 0>::bytes(nactive);
+    RCM_SHAPE(16, 128)
+    RCM_SHAPE(8, 128)
+    RCM_SHAPE(4, 128)
+    RCM_SHAPE(32, 192)
+    RCM_SHAPE(16, 96)
+#undef RCM_SHAPE
     return 0;
 }
 
 template <int MODE, int NACT, int C, int NT>
 static cudaError_t launch_t(const StepArgs& a, int nactive, int grid, cudaStream_t st) {
-    const size_t smem = Smem<C, NT>::bytes(nactive);
+    const size_t smem = Smem<C, NT, NACT>::bytes(nactive);
     auto kern = a.clampk ? rcm_step_kernel<MODE, NACT, C, NT, true> : rcm_step_kernel<MODE, NACT, C, NT, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -996,7 +1103,7 @@ cudaError_t rcm_launch_cplkavg(int n, const double* lo, const double* hi, const 
 }
 
 size_t rcm_lbl_smem_bytes(int C, int nthreads) {
-    return ((size_t)EXP_TAB * 32 + (size_t)NLAY * C * 3 + C + (size_t)NLEV * (nthreads / 2)) * sizeof(double);
+    return ((size_t)EXP_TAB * EXP_REP + (size_t)NLAY * C * 3 + C + (size_t)NLEV * (nthreads / 2)) * sizeof(double);
 }
 
 cudaError_t rcm_launch_lbl_step(const LblArgs& a, cudaStream_t st) {

@@ -13,6 +13,7 @@ constexpr int MAX_TPERT = 16;
 constexpr int HALF = NLAY / 2;     // layers owned by each lane of a pair
 constexpr int RCM_LBL_C = 16, RCM_LBL_NT = 128;  // tile shape of the LBL radiative-transfer kernel
 constexpr int EXP_TAB = 64;        // entries of the 2^(j/64) table used by the solver's exp
+constexpr int EXP_REP = 16;        // copies of every entry side by side: an LDS.64 is served per half-warp, lane l reads copy l & 15
 
 // Everything that is uniform over the ensemble.  Lives in __constant__ memory.
 struct DevConst {
@@ -47,6 +48,7 @@ struct StepArgs {
     int diag_ncol;       // columns of the whole ensemble = row length of diag
     int C;               // columns per tile
     int nthreads;        // threads per CTA (2 * C * wavelength groups)
+    int stage_rows;      // 1: the next wavelength's table rows travel into shared memory (cp.async.bulk) during the angle loop
     int clampk;          // 1: exp_scaled clamps its exponent itself (angle schedules where tau_clamp would bite)
     double tau_clamp;    // tau is clamped to this before the transmissions are evaluated (see exp_scaled)
     int ntiles;

@@ -194,6 +194,65 @@ def test_port_oracle_on_seeded_ensemble(solver, rcm, port, golden):
     np.testing.assert_allclose(st["Tlayer"], ref["Tlayer"], rtol=1e-10)
 
 
+@pytest.mark.parametrize("nangle,cubes,cloud", [(1, 1, 17), (7, 1, 17), (12, 0, -1), (45, 1, 3), (64, 1, 17), (30, 0, 17)])
+def test_other_quadratures_and_clouds_against_the_port(solver, rcm, port, golden, nangle, cubes, cloud):
+    """Consts the reference hard-codes, varied: number of angles (odd counts pad the chain schedule, without cubes
+    the exponent clamp moves into exp), cloud layer / no cloud; ragged ensemble (37 columns); three steps."""
+    atm = rcm.read_atm(table_path(20).replace("Reduced20Forcing.rcmtab", "column21.atm"))
+    pl = atm[:, 1]
+    Tlev, vlev = rcm.make_ensemble(37, 31 + nangle, pl, atm[:, 2], atm[:, 4:9].T.copy())
+    st0 = rcm.init_columns(pl, Tlev, vlev)
+    p = rcm.default_params()
+    p.solar_irr = float(golden["solar_irr"])
+    p.nangle, p.cloud_layer = nangle, cloud
+    solver.set_option(0, cubes)
+    solver.set_params(p)
+    try:
+        solver.set_repwvl_table_from(rcm.Table(table_path(20)))
+        solver.set_columns(pl, st0["Tlayer"], Tlev[:, 20], st0["vmr9"], st0["rel_hum"])
+        solver.advance(3)
+        st = solver.get_state()
+    finally:
+        solver.set_option(0, 1)
+        solver.set_params(rcm.default_params())
+    ref = port.advance(port.load_rcmtab(table_path(20)), pl, st0["rel_hum"], float(golden["solar_irr"]), st0["Tlayer"],
+                       Tlev[:, 20], st0["vmr9"], 3, nangle=nangle, cloud_layer=cloud)
+    assert relerr(st["E_up"], ref["E_up"]) < 1e-9
+    assert relerr(st["E_down"][:, 1:], ref["E_down"][:, 1:]) < 1e-9
+    np.testing.assert_allclose(st["Tlayer"], ref["Tlayer"], rtol=1e-10)
+    np.testing.assert_allclose(st["dt"], ref["dt"], rtol=1e-8)
+
+
+def test_row_staging_fallback_and_equivalence(solver, rcm, port, golden):
+    """K1 normally reads table rows staged in shared memory (three candidate temperature intervals per layer and
+    tile).  (1) Staged and unstaged K1 give bit-identical states.  (2) A tile whose columns span more than three
+    intervals takes the global-memory path: checked against the port."""
+    atm = rcm.read_atm(table_path(100).replace("Reduced100Forcing.rcmtab", "column21.atm"))
+    pl = atm[:, 1]
+    ncol = 50
+    Tlev, vlev = rcm.make_ensemble(ncol, 5, pl, atm[:, 2], atm[:, 4:9].T.copy())
+    wild = Tlev + np.linspace(-55.0, 55.0, ncol)[:, None]          # 110 K across every 16-column tile
+    solver.set_repwvl_table_from(rcm.Table(table_path(100)))
+    res = {}
+    for name, T in (("mild", Tlev), ("wild", wild)):
+        st0 = rcm.init_columns(pl, T, vlev)
+        for staged in (1, 0):
+            solver.set_option(3, staged)
+            solver.set_columns(pl, st0["Tlayer"], T[:, 20], st0["vmr9"], st0["rel_hum"])
+            solver.advance(2)
+            res[name, staged] = solver.get_state()
+        solver.set_option(3, 1)
+        for k in ("E_up", "E_down", "Tlayer", "dt"):
+            assert np.array_equal(res[name, 1][k], res[name, 0][k]), (name, k)
+        ref = port.advance(port.load_rcmtab(table_path(100)), pl, st0["rel_hum"], float(golden["solar_irr"]),
+                           st0["Tlayer"], T[:, 20], st0["vmr9"], 2)
+        assert relerr(res[name, 1]["E_up"], ref["E_up"]) < 1e-9
+        np.testing.assert_allclose(res[name, 1]["Tlayer"], ref["Tlayer"], rtol=1e-10)
+    tau, lp, lt = solver.build_tau()                               # of the wild ensemble after two steps
+    lt = lt[:48].reshape(3, 16, 20)
+    assert (lt.max(axis=1) - lt.min(axis=1)).max() >= 3, "the wild ensemble must exercise the fallback"
+
+
 def test_full_size_properties(solver, rcm, golden):
     """BASELINE-size ensemble (65,536 columns x 100 wavelengths): size-independent properties.
     (1) replicated columns give bit-identical results wherever they sit in the ensemble;

@@ -16,9 +16,9 @@ pl = atm[:, 1]
 Tlev, vlev = rcm.make_ensemble(ncol, 12345, pl, atm[:, 2], atm[:, 4:9].T.copy())
 st0 = rcm.init_columns(pl, Tlev, vlev)
 s.set_repwvl_table_from(rcm.Table(os.path.join(G, f"Reduced{nw}Forcing.rcmtab")))
-cfgs = [int(a) for a in sys.argv[3:]] or [0, 1, 4, 5]
-for cfg in cfgs:
-    s.set_option(1, cfg)
+cfgs = [tuple(int(x) for x in a.split(',')) for a in sys.argv[3:]] or [(1, 1), (1, 0)]
+for cfg, pf in cfgs:
+    s.set_option(1, cfg); s.set_option(3, pf)
     s.set_columns(pl, st0["Tlayer"], np.full(ncol, 288.2), st0["vmr9"], st0["rel_hum"])
     s.advance(2)
     s.kernel_time_ms(reset=True)
@@ -29,7 +29,7 @@ for cfg in cfgs:
     ms, n = s.kernel_time_ms(reset=True)
     units = ncol * nw * 20
     olr = s.get_state()["E_up"][0, 0]
-    print(f"shape={cfg} ncol={ncol} nwvl={nw}: kernel {ms:.3f} ms/step ({n} launches), wall {wall*1e3:.3f} ms/step, "
+    print(f"shape={cfg} stage_rows={pf} ncol={ncol} nwvl={nw}: kernel {ms:.3f} ms/step ({n} launches), wall {wall*1e3:.3f} ms/step, "
           f"{units/ms/1e6:.2f} Gunits/s  OLR[0]={olr:.10f}", flush=True)
     s.kernel_time_ms(reset=True)
     s.advance(10, want_scalars=False); s.synchronize()

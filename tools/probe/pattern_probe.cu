@@ -6,10 +6,10 @@
 namespace {
 template <int WHICH>
 __global__ void __launch_bounds__(192, 2) pat(double* out, int iters, const double* tab) {
-    __shared__ double stab[EXP_TAB * 32];
-    for (int i = threadIdx.x; i < EXP_TAB * 32; i += blockDim.x) stab[i] = tab[i >> 5];
+    __shared__ double stab[EXP_TAB * EXP_REP];
+    for (int i = threadIdx.x; i < EXP_TAB * EXP_REP; i += blockDim.x) stab[i] = tab[i / EXP_REP];
     __syncthreads();
-    const unsigned tl = (unsigned)__cvta_generic_to_shared(stab + (threadIdx.x & 31));
+    const unsigned tl = (unsigned)__cvta_generic_to_shared(stab + (threadIdx.x & (EXP_REP - 1)));
     double tau[HALF], D1[HALF], E1[HALF], E2[HALF], tA[HALF], tB[HALF];
 #pragma unroll
     for (int j = 0; j < HALF; ++j) {
