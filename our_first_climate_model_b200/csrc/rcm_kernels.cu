@@ -30,42 +30,44 @@ namespace {
 
 // ------------------------------------------------------------------------------------------
 // exp of (a*b) for the transmissions t = exp(-tau/mu) and the Planck exponent.  With
-// z = a*b*64/ln2 (the caller passes b already scaled by 64/ln2), k = round(z), f = z - k:
-//   exp = 2^(k>>6) * 2^((k&63)/64) * exp(f*ln2/64),  |f| <= 1/2,
-// exp(f*c) - 1 = f*h(f) with a degree-4 Horner h (truncation 3.5e-17 relative).
-// 9 FP64-pipe instructions + 4 others (LOP3, LEA, LDS.64, LEA).  Non-FP64 instructions are not free
-// next to DFMA on this GPU (tools/probe/issue_probe.cu: each costs ~0.75 issue cycles, a DFMA 2), hence:
-//  * the 64-entry table 2^(j/64) is replicated per lane (tab[j*32 + lane]): the LDS.64 never bank-conflicts;
+// z = a*b*128/ln2 (the caller passes b already scaled by 128/ln2), k = round(z), f = z - k:
+//   exp = 2^(k>>7) * 2^((k&127)/128) * exp(f*ln2/128),  |f| <= 1/2,
+// exp(f*c) - 1 = f*h(f) with a degree-3 Horner h: the Taylor polynomial of degree 5 with its last term
+// economised onto the lower ones (Chebyshev), 7.6e-17 relative - below half an ulp.
+// 8 FP64-pipe instructions + 4 others (LOP3, IMAD, LDS.64, IMAD).  Non-FP64 instructions are not free
+// next to DFMA on this GPU (tools/probe/issue_probe.cu: each costs ~0.7-1.5 issue cycles, a DFMA 2), hence:
+//  * the 128-entry table 2^(j/128) holds EXP_REP = 8 copies of every entry side by side (lane l reads copy l & 7):
+//    an LDS.64 is served per half-warp, so at worst two lanes of a half-warp meet in a bank (measured: the same
+//    rate as with 16 or 32 copies) and the table stays at 8 KB;
 //  * the power of two is applied to the TABLE VALUE with one integer multiply-add on its high word,
-//    hi += k << 14.  Since k = 64 m + j, k << 14 = (m << 20) + (j << 14): the table entries are stored
-//    with j << 14 pre-subtracted from their high word (rcm_create), so no shift/mask of k is needed;
-//  * no clamp of the exponent: the caller guarantees |k >> 6| <= 1000 (tau is clamped once per layer,
+//    hi += k << 13.  Since k = 128 m + j, k << 13 = (m << 20) + (j << 13): the table entries are stored
+//    with j << 13 pre-subtracted from their high word (rcm_create), so no shift/mask of k is needed;
+//  * no clamp of the exponent: the caller guarantees |k >> 7| <= 1000 (tau is clamped once per layer,
 //    StepArgs::tau_clamp), unless CLAMPK, which clamps k here for angle schedules that need it.
 // ------------------------------------------------------------------------------------------
 template <bool CLAMPK>
-__device__ __forceinline__ double exp_scaled(double a, double b_l2e64, unsigned tab_lane) {
+__device__ __forceinline__ double exp_scaled(double a, double b_l2e, unsigned tab_lane) {
     const double SHIFT = 6755399441055744.0;  // 1.5 * 2^52: the add leaves round(z) in the low word
-    const double t = fma(a, b_l2e64, SHIFT);
+    const double t = fma(a, b_l2e, SHIFT);
     int k = __double2loint(t);
     const double kd = t - SHIFT;
-    const double f = fma(a, b_l2e64, -kd);  // exact product minus an integer: one rounding
-    if (CLAMPK) k = max(k, -64000);
-    double Ts;  // tab_lane: shared-window byte address of this lane's copy of entry 0 (entries are 256 B apart)
-    asm("{\n\t.reg .b32 j, ad;\n\tand.b32 j, %1, 63;\n\tmad.lo.u32 ad, j, %3, %2;\n\tld.shared.f64 %0, [ad];\n\t}"
+    const double f = fma(a, b_l2e, -kd);  // exact product minus an integer: one rounding
+    if (CLAMPK) k = max(k, -1000 * EXP_TAB);
+    double Ts;  // tab_lane: shared-window byte address of this lane's copy of entry 0 (entries are EXP_REP * 8 bytes apart)
+    asm("{\n\t.reg .b32 j, ad;\n\tand.b32 j, %1, %4;\n\tmad.lo.u32 ad, j, %3, %2;\n\tld.shared.f64 %0, [ad];\n\t}"
         : "=d"(Ts)
-        : "r"(k), "r"(tab_lane), "n"(EXP_REP * 8));
-    const double T = __hiloint2double(__double2hiint(Ts) + (k << 14), __double2loint(Ts));  // 2^(k/64)
-    // Horner coefficients c^5/120, c^4/24, c^3/6, c^2/2, c (c = ln2/64) come from the constant bank: as
-    // literals each block of ten exp's would re-materialise them into uniform registers (10 UMOV per block)
-    double h = fma(f, cst.expc[0], cst.expc[1]);
-    h = fma(f, h, cst.expc[2]);
-    h = fma(f, h, cst.expc[3]);
-    h = fma(f, h, cst.expc[4]);
+        : "r"(k), "r"(tab_lane), "n"(EXP_REP * 8), "n"(EXP_TAB - 1));
+    const double T = __hiloint2double(__double2hiint(Ts) + (k << (20 - EXP_LOG2)), __double2loint(Ts));  // 2^(k/128)
+    // Horner coefficients from the constant bank: as literals each block of ten exp's would re-materialise them
+    // into uniform registers (10 UMOV per block)
+    double h = fma(f, cst.expc[3], cst.expc[2]);
+    h = fma(f, h, cst.expc[1]);
+    h = fma(f, h, cst.expc[0]);
     const double u = T * f;
     return fma(u, h, T);
 }
 
-constexpr double L2E64 = 0x1.71547652b82fep+6;  // 64/ln2
+constexpr double L2E64 = 0x1.71547652b82fep+7;  // EXP_TAB / ln2  (name kept: "scaled log2(e)")
 
 // a / d for normal, finite d: hardware reciprocal seed (>= 20 bits) + one Newton step (40 bits) + one
 // residual correction of the quotient (<= 1 ulp).  5 FP64-pipe instructions, no special-case branches

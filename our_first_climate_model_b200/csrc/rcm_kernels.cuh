@@ -12,8 +12,8 @@ constexpr int MAX_ANGLE = 64;
 constexpr int MAX_TPERT = 16;
 constexpr int HALF = NLAY / 2;     // layers owned by each lane of a pair
 constexpr int RCM_LBL_C = 16, RCM_LBL_NT = 128;  // tile shape of the LBL radiative-transfer kernel
-constexpr int EXP_TAB = 64;        // entries of the 2^(j/64) table used by the solver's exp
-constexpr int EXP_REP = 16;        // copies of every entry side by side: an LDS.64 is served per half-warp, lane l reads copy l & 15
+constexpr int EXP_LOG2 = 7, EXP_TAB = 1 << EXP_LOG2;  // entries of the 2^(j/128) table used by the solver's exp
+constexpr int EXP_REP = 8;         // copies of every entry side by side, lane l reads copy l & 7 (see exp_scaled)
 
 // Everything that is uniform over the ensemble.  Lives in __constant__ memory.
 struct DevConst {
@@ -38,7 +38,7 @@ struct DevConst {
     double neg_inv_mu_l2e[MAX_ANGLE + 2];  // per CHAIN: -1/mu of its head, times 64/ln2 (argument scaling of exp_scaled)
     double cmu[MAX_ANGLE + 2];             // per SLOT: 2*pi*mu*dmu (0 for a padding slot)
     double csum;                           // sum of cmu over all nodes
-    double expc[5];                        // Horner coefficients of exp_scaled
+    double expc[4];                        // Horner coefficients of exp_scaled, lowest order first
     // LBL band edges etc. live in global memory
 };
 
