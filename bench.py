@@ -304,6 +304,146 @@ def run_b200(args, rank, world, local_rank):
     return 0
 
 
+# ------------------------------------------------------------------------------------------------------
+# Optional second workload (--workload lbl): BASELINE configs[4], a 4,096-column line-by-line ensemble with 2xCO2
+# forcing, columns sharded over the ranks (total fixed: strong scaling).  The reference's LBL tables are not
+# distributed: synthetic tables in its format (rcm_make_lbl_tables), --lbl-nwvl wavelengths.
+# ------------------------------------------------------------------------------------------------------
+LBL_EXEC_FP64_PER_UNIT = 527.9  # ncu, rcm_lbl_rt_kernel, 512 columns x 20,000 wavelengths (profiles/r1c_lbl_kernel.md)
+
+
+def build_lbl_case(rcm, ncol, nwvl, seed):
+    atm = rcm.read_atm(os.path.join(GOLDEN, "column21.lbl.atm"))
+    full = rcm.read_atm(os.path.join(GOLDEN, "column21.atm"))
+    pl = atm[:, 1].copy()
+    Tlev, vlev = rcm.make_ensemble(ncol, seed, pl, atm[:, 2].copy(), full[:, 4:9].T.copy())
+    st = rcm.init_columns(pl, Tlev, vlev, 1.0)  # 2xCO2 enters through co2_factor of the LBL tables
+    base = rcm.init_columns(pl, atm[None, :, 2].copy(), full[None, :, 4:9].transpose(0, 2, 1).copy(), 1.0)
+    h2o_ref, o3_ref = base["vmr9"][0, 0].copy(), base["vmr9"][0, 2].copy()
+    wvl, tau5 = rcm.make_lbl_tables(nwvl, 777, pl, h2o_ref, o3_ref)
+    return dict(pl=pl, st=st, Tsurf=Tlev[:, 20].copy(), wvl=wvl, tau5=tau5, h2o_ref=h2o_ref, o3_ref=o3_ref)
+
+
+def _lbl_cpu_worker(args):
+    seed, ncol, nwvl = args
+    import our_first_climate_model_b200 as rcm
+    from oracle import port as P
+    c = build_lbl_case(rcm, ncol, nwvl, seed)
+    solar = rcm.solar_setup()["solar_irr"]
+    t0 = time.perf_counter()
+    P.lbl_advance(c["wvl"], c["tau5"], c["pl"], c["st"]["rel_hum"], c["h2o_ref"], c["st"]["vmr9"][:, 2] / c["o3_ref"], 2.0,
+                  solar, c["st"]["Tlayer"], c["Tsurf"], c["st"]["vmr9"][:, 0], 1)
+    return time.perf_counter() - t0
+
+
+def run_b200_lbl(args, rank, world, local_rank):
+    import torch
+    import our_first_climate_model_b200 as rcm
+    from our_first_climate_model_b200 import distributed as rdist
+    if not torch.cuda.is_available() or rcm.device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device - the solver has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        rdist.init("nccl")
+    total, nwvl = args.lbl_ncol, args.lbl_nwvl
+    lo, hi = rdist.shard_range(total, rank, world)
+    ncol = hi - lo
+    c = build_lbl_case(rcm, total, nwvl, 4242)
+    sl = slice(lo, hi)
+    solver = rcm.Solver(local_rank)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    solver.set_stream(stream.cuda_stream)
+    solver.set_lbl_tables(c["wvl"], c["tau5"], c["h2o_ref"], c["o3_ref"], 2.0)
+    solver.set_columns(c["pl"], c["st"]["Tlayer"][sl], c["Tsurf"][sl], c["st"]["vmr9"][sl], c["st"]["rel_hum"][sl])
+    exch = rdist.StepScalarExchange(torch.device("cuda", local_rank))
+    peak = solver.fp64_microbench(0) if rank == 0 else 0.0
+
+    def one_step():
+        exch.submit(rdist.device_view(solver.advance_async(1), 4))
+
+    for _ in range(args.warmup):
+        one_step()
+    exch.latest()
+    torch.cuda.synchronize()
+    l0 = solver.launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        rdist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        one_step()
+    scal = exch.latest()
+    e1.record(stream)
+    if world > 1:
+        rdist.barrier()
+    torch.cuda.synchronize()
+    ms_total = rdist.max_over_ranks(e0.elapsed_time(e1)) if world > 1 else e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = solver.launch_count() - l0
+    units_per_step = total * nwvl * NLAY
+    value = units_per_step * args.steps / (ms_total * 1e-3)
+    # e2e: host buffers through rcm_step_host (T, Tsurf, active VMRs up; fluxes, heating rates, T down)
+    nact = solver.nactive
+    pin = lambda *shape: torch.empty(*shape, dtype=torch.float64).pin_memory()
+    T_in, Ts_in, v_in = pin(ncol, NLAY), pin(ncol), pin(ncol, nact, NLAY)
+    Ed, Eu, dE, T_out, Ts_out = pin(ncol, 21), pin(ncol, 21), pin(ncol, NLAY), pin(ncol, NLAY), pin(ncol)
+    T_in.copy_(torch.from_numpy(c["st"]["Tlayer"][sl]))
+    Ts_in.copy_(torch.from_numpy(c["Tsurf"][sl]))
+    active = [k for k in range(9) if solver.params.species_mask >> k & 1]
+    v_in.copy_(torch.from_numpy(np.ascontiguousarray(c["st"]["vmr9"][sl][:, active, :])))
+    ptrs = [t.data_ptr() for t in (T_in, Ts_in, v_in, Ed, Eu, dE, T_out, Ts_out)]
+    h2d = (T_in.numel() + Ts_in.numel() + v_in.numel()) * 8
+    d2h = (Ed.numel() + Eu.numel() + dE.numel() + T_out.numel() + Ts_out.numel()) * 8
+    solver.step_host_ptrs(*ptrs)
+    if world > 1:
+        rdist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        solver.step_host_ptrs(*ptrs)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e_s = rdist.max_over_ranks(e2e_s) if world > 1 else e2e_s
+    if rank != 0:
+        return 0
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        import multiprocessing as mp
+        cores = len(os.sched_getaffinity(0))
+        cols = 32
+        with mp.get_context("fork").Pool(cores) as pool:
+            pool.map(_lbl_cpu_worker, [(1, 1, 200)] * cores)
+            t0 = time.perf_counter()
+            pool.map(_lbl_cpu_worker, [(100 + i, cols, nwvl) for i in range(cores)])
+            wall = time.perf_counter() - t0
+        cpu = {"value": cores * cols * nwvl * NLAY / wall, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{cols} columns x 1 step per core of the oracle's LBL composition (the reference has no LBL driver), "
+                         f"{wall:.1f} s wall"}
+    achieved = value / world * LBL_EXEC_FP64_PER_UNIT / 1e9
+    line = {"metric": "column*wavelength*layer flux updates/s (line-by-line RCE step)", "value": value, "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{total}-column line-by-line ensemble, 2xCO2, {nwvl} synthetic wavelengths "
+                                   "(BASELINE configs[4]); columns sharded over the ranks", "columns_total": total,
+                       "nwvl": nwvl, "nlayer": NLAY, "nangle": 30, "parallelism": f"{world} GPU(s)",
+                       "l2": "tables (5 x nwvl x 20 doubles = 16 MB at 20,000 wavelengths) are re-read by every tile: L2-resident"},
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "G FP64-pipe instr/s",
+                         "frac": achieved / peak if peak else None, "traffic": None, "kernel": "rcm_lbl_rt_kernel",
+                         "executed_fp64_instr_per_unit": LBL_EXEC_FP64_PER_UNIT},
+            "cpu_baseline": cpu,
+            "e2e": {"value": units_per_step * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps, "api": "rcm_step_host"},
+            "gpu_launches": launches, "clocks": clocks,
+            "ensemble": {"toa_net_mean_Wm2": float(scal[0]) / total}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -315,6 +455,10 @@ def main():
     ap.add_argument("--cpu-cols", type=int, default=None, help="columns per core in a CPU sample")
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="repwvl", choices=["repwvl", "lbl"],
+                    help="repwvl = the headline metric (BASELINE configs[3]); lbl = configs[4], optional")
+    ap.add_argument("--lbl-ncol", type=int, default=4096, help="columns of the LBL ensemble (all ranks together)")
+    ap.add_argument("--lbl-nwvl", type=int, default=20000)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
@@ -330,6 +474,8 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)
+    if args.workload == "lbl":
+        return run_b200_lbl(args, rank, world, local_rank)
     return run_b200(args, rank, world, local_rank)
 
 
