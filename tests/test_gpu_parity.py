@@ -223,6 +223,43 @@ def test_other_quadratures_and_clouds_against_the_port(solver, rcm, port, golden
     np.testing.assert_allclose(st["dt"], ref["dt"], rtol=1e-8)
 
 
+def test_other_species_masks_and_extreme_profiles(solver, rcm, port, golden):
+    """(1) species_mask other than the default five (generic-species kernel instantiation, no row staging): only H2O and
+    CO2 absorb, the other VMRs are zero as the mask requires.  (2) Far-from-standard profiles: +-60 K offsets with
+    vertical structure, VMRs scaled by 10^U(-1,1), no ozone in some columns - table lookups run out of range
+    (LowerPos semantics) and tau spans many decades."""
+    atm = rcm.read_atm(table_path(20).replace("Reduced20Forcing.rcmtab", "column21.atm"))
+    pl = atm[:, 1]
+    rng = np.random.default_rng(11)
+    ncol = 45
+    Tlev = atm[:, 2][None, :] + rng.uniform(-60, 60, (ncol, 1)) + 15 * np.sin(np.linspace(0, 3, 21))[None, :] * rng.uniform(-1, 1, (ncol, 1))
+    vlev = np.tile(atm[:, 4:9].T[None], (ncol, 1, 1)) * 10 ** rng.uniform(-1, 1, (ncol, 5, 1))
+    vlev[::7, 1] = 0.0
+    st0 = rcm.init_columns(pl, Tlev, vlev)
+    tab = port.load_rcmtab(table_path(20))
+    solar = float(golden["solar_irr"])
+    for mask in (0x2F, 0x03):
+        vm = st0["vmr9"].copy()
+        for k in range(9):
+            if not mask >> k & 1:
+                vm[:, k] = 0.0
+        p = rcm.default_params()
+        p.solar_irr, p.species_mask = solar, mask
+        solver.set_params(p)
+        try:
+            solver.set_repwvl_table_from(rcm.Table(table_path(20)))
+            solver.set_columns(pl, st0["Tlayer"], Tlev[:, 20], vm, st0["rel_hum"])
+            solver.advance(2)
+            st = solver.get_state()
+        finally:
+            solver.set_params(rcm.default_params())
+        ref = port.advance(tab, pl, st0["rel_hum"], solar, st0["Tlayer"], Tlev[:, 20], vm, 2)
+        assert relerr(st["E_up"], ref["E_up"]) < 1e-9, hex(mask)
+        assert relerr(st["E_down"][:, 1:], ref["E_down"][:, 1:]) < 1e-9, hex(mask)
+        np.testing.assert_allclose(st["Tlayer"], ref["Tlayer"], rtol=1e-10)
+        np.testing.assert_allclose(st["h2o"], ref["vmr9"][:, 0], rtol=1e-10)
+
+
 def test_row_staging_fallback_and_equivalence(solver, rcm, port, golden):
     """K1 normally reads table rows staged in shared memory (three candidate temperature intervals per layer and
     tile).  (1) Staged and unstaged K1 give bit-identical states.  (2) A tile whose columns span more than three
