@@ -165,6 +165,7 @@ __device__ __forceinline__ void sweep_item(const double (&tau)[HALF], const doub
     int slot = 0;
     auto chain = [&](double (&tc)[HALF], double (&tn)[HALF], int ic) {
         const int len = cst.chain_len[ic];
+#pragma unroll 1
         for (int k = 1; k < len; ++k) {
             sweep(tc, cst.cmu[slot++]);
 #pragma unroll
