@@ -270,6 +270,7 @@ class Solver:
             _check(st)
         self.ncol = 0
         self.nwvl = 0
+        self.stream_ptr = None
         self.nactive = bin(self.params.species_mask).count("1")
 
     # lifecycle
@@ -294,6 +295,7 @@ class Solver:
 
     def set_stream(self, stream_ptr: int | None):
         _check(_lib.rcm_set_stream(self._h, C.c_void_p(stream_ptr or 0)), self._h)
+        self.stream_ptr = stream_ptr or None  # None: the solver's own stream (the legacy stream 0 cannot be borrowed)
 
     def synchronize(self):
         _check(_lib.rcm_synchronize(self._h), self._h)

@@ -140,6 +140,10 @@ def run_to_equilibrium(solver, ncol_total: int, max_steps: int, check_every: int
     (one launch per block, nothing crosses GPUs meanwhile); after each block ONE allreduce of the block's scalars
     decides - identically on every rank - whether the whole ensemble is stationary (n_converged == ncol_total).
     With one rank this is rcm_run_to_equilibrium."""
+    if torch.cuda.is_available() and getattr(solver, "stream_ptr", None) != torch.cuda.current_stream().cuda_stream:
+        # the scalars are reduced by torch / NCCL on torch's current stream: the kernels must be queued on the same one
+        raise RuntimeError("run_to_equilibrium: call solver.set_stream(s.cuda_stream) with a torch.cuda.Stream s that is "
+                           "torch's current stream (the legacy default stream cannot be shared with the solver)")
     done = 0
     means = None
     while done < max_steps:

@@ -1,0 +1,71 @@
+"""BASELINE configs[3] over N GPUs: ONE 65,536-column synthetic ensemble (repwvl-100) sharded across the ranks of a
+torchrun launch and stepped until every column is stationary (strong scaling: total work fixed).
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29555 \
+        tools/equilibrium_run_dist.py [ncol_total] [max_steps] [threshold_K_per_step] [check_every]
+
+Every rank generates the same ensemble (seeded) and keeps its contiguous shard; between checks nothing crosses
+GPUs; each check is one allreduce of the block's four scalars (distributed.run_to_equilibrium).  Time is the maximum
+over the ranks of the CUDA-event time around the loop.  Rank 0 prints one JSON line."""
+import json, os, sys
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import numpy as np
+import torch
+import our_first_climate_model_b200 as rcm
+from our_first_climate_model_b200 import distributed as rdist
+import bench
+
+ncol = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
+max_steps = int(sys.argv[2]) if len(sys.argv) > 2 else 6000
+thr = float(sys.argv[3]) if len(sys.argv) > 3 else 1e-3
+check_every = int(sys.argv[4]) if len(sys.argv) > 4 else 250
+
+world = int(os.environ.get("WORLD_SIZE", 1))
+local = int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local)
+rank = 0
+if world > 1:
+    rank, world = rdist.init("nccl")
+lo, hi = rdist.shard_range(ncol, rank, world)
+st = bench.build_ensemble(rcm, ncol, 12345)
+p = rcm.default_params()
+p.dT_converged = thr
+s = rcm.Solver(local, p)
+stream = torch.cuda.Stream()  # the solver launches on this torch stream: events and NCCL see its work
+torch.cuda.set_stream(stream)
+s.set_stream(stream.cuda_stream)
+s.set_repwvl_table_from(rcm.Table(os.path.join(bench.GOLDEN, "Reduced100Forcing.rcmtab")))
+s.set_columns(st["plevel"], st["Tlayer"][lo:hi].copy(), st["Tsurf"][lo:hi].copy(),
+              np.ascontiguousarray(st["vmr9"][lo:hi]), st["rel_hum"][lo:hi].copy())
+s.advance(1)  # warm-up launch (module load, shared-memory attribute), then restart from the initial state
+s.set_columns(st["plevel"], st["Tlayer"][lo:hi].copy(), st["Tsurf"][lo:hi].copy(),
+              np.ascontiguousarray(st["vmr9"][lo:hi]), st["rel_hum"][lo:hi].copy())
+rdist.barrier()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(stream)
+res = rdist.run_to_equilibrium(s, ncol, max_steps, check_every)
+e1.record(stream)
+torch.cuda.synchronize()
+ms = rdist.max_over_ranks(e0.elapsed_time(e1))
+out = s.get_state()
+tsum = torch.tensor([out["Tsurf"].sum(), out["Tsurf"].min() * -1.0, out["Tsurf"].max()], dtype=torch.float64, device="cuda")
+if world > 1:
+    import torch.distributed as dist
+    mm = tsum[1:].clone()
+    dist.all_reduce(tsum[:1], op=dist.ReduceOp.SUM)
+    dist.all_reduce(mm, op=dist.ReduceOp.MAX)
+    tsum[1:] = mm
+if rank == 0:
+    steps = res["steps"]
+    print(json.dumps({"tool": "equilibrium_run_dist", "n_gpus": world, "ncol_total": ncol, "steps": steps,
+                      "check_every": check_every, "threshold_K_per_step": thr, "seconds": ms / 1e3,
+                      "ms_per_step": ms / steps, "updates_per_s": ncol * 100.0 * 20 * steps / (ms / 1e3),
+                      "converged_fraction": res["converged_fraction"], "max_dT": res["max_dT"],
+                      "toa_net_mean_Wm2": res["toa_net_mean"], "Tsurf_mean": float(tsum[0]) / ncol,
+                      "Tsurf_min": -float(tsum[1]), "Tsurf_max": float(tsum[2]),
+                      "member0_Tsurf": float(out["Tsurf"][0])}))
+s.close()
+if world > 1:
+    rdist.barrier()
+    torch.distributed.destroy_process_group()
