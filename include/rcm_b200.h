@@ -161,6 +161,15 @@ int rcm_set_columns(rcm_solver* s, int ncol, const double* plevel_hPa, const dou
                     const double* Tsurf, const double* vmr9, const double* rel_hum);
 /* Compact per-step upload for resident ensembles: only T, Tsurf and the H2O..CH4 rows named in
  * species_mask (vmr_active [ncol][n_active][20], ascending species index).  Keeps plevel/rel_hum. */
+/* Per-column solar forcing, computed on the device: doubling_adding + solar_radiative_transfer_setup
+ * (main.cpp:214-264) with one cloud optical depth / zenith cosine / surface albedo per column.  tau_s, mu_s, albedo:
+ * host arrays [ncol] or NULL (then the scalar in *sp).  From the next step on, column c is heated by its own
+ * solar_irr[c] instead of rcm_params::solar_irr (main.cpp:341); with cloud_from_tau_s != 0 the thermal grey cloud of
+ * column c becomes tau_s[c] / 2 instead of rcm_params::cloud_tau (main.cpp:266-274).  Optional outputs (host, [ncol]):
+ * solar_irr_out, r_total_out (planetary albedo).  sp == NULL switches back to the ensemble-wide constants.
+ * rcm_set_columns() drops the per-column forcing: call this after it. */
+int rcm_set_column_solar(rcm_solver* s, const rcm_solar_params* sp, const double* tau_s, const double* mu_s,
+                         const double* albedo, int cloud_from_tau_s, double* solar_irr_out, double* r_total_out);
 int rcm_update_columns(rcm_solver* s, const double* Tlayer, const double* Tsurf, const double* vmr_active);
 int rcm_set_step_index(rcm_solver* s, long step_index);
 

@@ -330,6 +330,22 @@ class Solver:
                                     _p(_f64(vmr9, (n, NSPEC, NLAY))), _p(_f64(rel_hum, (n, NLAY)))), self._h)
         self.ncol = n
 
+    def set_column_solar(self, sp: SolarParams | None = None, tau_s=None, mu_s=None, albedo=None,
+                         cloud_from_tau_s: bool = False, clear: bool = False) -> dict | None:
+        """rcm_set_column_solar: per-column solar forcing (and optionally the thermal grey cloud) computed on the
+        device; returns {'solar_irr', 'r_total'} per column.  clear=True: back to the ensemble-wide constants."""
+        if clear:
+            _check(_lib.rcm_set_column_solar(self._h, None, None, None, None, C.c_int(0), None, None), self._h)
+            return None
+        sp = sp or default_solar_params()
+        n = self.ncol
+        arr = [None if a is None else _f64(np.broadcast_to(a, (n,))) for a in (tau_s, mu_s, albedo)]
+        out = dict(solar_irr=np.zeros(n), r_total=np.zeros(n))
+        _check(_lib.rcm_set_column_solar(self._h, C.byref(sp), _p(arr[0]), _p(arr[1]), _p(arr[2]),
+                                         C.c_int(1 if cloud_from_tau_s else 0), _p(out["solar_irr"]),
+                                         _p(out["r_total"])), self._h)
+        return out
+
     def update_columns(self, Tlayer=None, Tsurf=None, vmr_active=None):
         a = None if Tlayer is None else _f64(Tlayer, (self.ncol, NLAY))
         b = None if Tsurf is None else _f64(Tsurf, (self.ncol,))

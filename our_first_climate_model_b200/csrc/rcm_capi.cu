@@ -44,6 +44,8 @@ struct rcm_solver {
     double *d_Ed = nullptr, *d_Eu = nullptr, *d_dE = nullptr, *d_dt = nullptr;
     double *d_diag = nullptr, *d_scalars = nullptr, *d_tau = nullptr, *d_red = nullptr;
     int* d_lowpos = nullptr;
+    double *d_solar_col = nullptr, *d_cloud_col = nullptr;  // per-column solar forcing / cloud tau (rcm_set_column_solar)
+    bool has_col_solar = false, has_col_cloud = false;
     size_t diag_steps = 0, tau_cap = 0;
     long step_index = 0;
     bool tau_valid = false;
@@ -342,6 +344,8 @@ int launch_part(rcm_solver* s, int mode, int nsteps, bool want_diag, const Part&
     a.lowpos_t = s->d_lowpos + o * NLAY;
     a.exp_tab = s->d_exp_tab;
     a.h2o_slot = s->h2o_slot;
+    a.solar_col = s->has_col_solar ? s->d_solar_col + o : nullptr;
+    a.cloud_col = s->has_col_cloud ? s->d_cloud_col + o : nullptr;
     int per_sm = p.sh.per_sm;
     if (rcm_step_smem_bytes(a.C, s->nactive, a.nthreads) * per_sm > 224 * 1024) per_sm = 1;
     const int ctas = nsm * per_sm;
@@ -437,7 +441,7 @@ int rcm_destroy(rcm_solver* s) {
     void* ptrs[] = {s->d_xsec_file, s->d_coef, s->d_species, s->d_planck_c, s->d_planck_k, s->d_exp_tab, s->d_T, s->d_Ts, s->d_vmr, s->d_rh,
                     s->d_Tprev, s->d_time, s->d_lbl_lo, s->d_lbl_hi, s->d_lbl_tau5, s->d_lbl_h2o_ref, s->d_lbl_o3_ref, s->d_sH, s->d_sO,
                     s->d_dTstat, s->d_part, s->d_Ed, s->d_Eu, s->d_dE, s->d_dt, s->d_diag, s->d_scalars, s->d_red, s->d_tau,
-                    s->d_lowpos};
+                    s->d_lowpos, s->d_solar_col, s->d_cloud_col};
     for (void* q : ptrs)
         if (q) cudaFree(q);
     for (auto& e : s->ev_free) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -633,6 +637,64 @@ int rcm_set_columns(rcm_solver* s, int ncol, const double* plevel_hPa, const dou
     CU(cudaStreamSynchronize(s->stream));
     s->step_index = 0;
     s->tau_valid = false;
+    s->has_col_solar = s->has_col_cloud = false;  // per-column forcing belongs to the column set it was given for
+    return RCM_OK;
+}
+
+int rcm_set_column_solar(rcm_solver* s, const rcm_solar_params* sp, const double* tau_s, const double* mu_s,
+                         const double* albedo, int cloud_from_tau_s, double* solar_irr_out, double* r_total_out) {
+    if (!s) return RCM_ERR_ARG;
+    if (s->ncol <= 0) return fail(s, RCM_ERR_STATE, "rcm_set_columns first");
+    CU(cudaSetDevice(s->device));
+    if (!sp) {  // back to the ensemble-wide constants of rcm_params
+        s->has_col_solar = s->has_col_cloud = false;
+        s->tau_valid = false;
+        return RCM_OK;
+    }
+    if (sp->doublings < 0 || sp->doublings > 60) return fail(s, RCM_ERR_ARG, "doublings must be in 0..60");
+    if (cloud_from_tau_s && s->p.cloud_layer < 0) return fail(s, RCM_ERR_ARG, "cloud_from_tau_s needs a cloud layer");
+    const size_t n = (size_t)s->ncol;
+    if (!s->d_solar_col) {
+        CU(dalloc(s->d_solar_col, (size_t)s->cap));
+        CU(dalloc(s->d_cloud_col, (size_t)s->cap));
+    }
+    // inputs travel through one scratch allocation [3][n]; r_total comes back through its first row
+    double* d_in = nullptr;
+    CU(cudaMalloc((void**)&d_in, 3 * n * sizeof(double)));
+    const double* src[3] = {tau_s, mu_s, albedo};
+    for (int k = 0; k < 3; ++k)
+        if (src[k]) {
+            cudaError_t e = cudaMemcpyAsync(d_in + k * n, src[k], n * sizeof(double), cudaMemcpyHostToDevice, s->stream);
+            if (e != cudaSuccess) { cudaFree(d_in); return cuda_fail(s, e, "upload solar inputs"); }
+        }
+    double* d_rt = nullptr;
+    if (r_total_out) {
+        cudaError_t e = cudaMalloc((void**)&d_rt, n * sizeof(double));
+        if (e != cudaSuccess) { cudaFree(d_in); return cuda_fail(s, e, "cudaMalloc"); }
+    }
+    SolarArgs a{};
+    a.n = s->ncol;
+    a.doublings = sp->doublings;
+    a.tau_s = sp->tau_s; a.mu_s = sp->mu_s; a.g_asym = sp->g_asym; a.albedo = sp->albedo; a.daytime = sp->daytime; a.E_0 = sp->E_0;
+    a.tau_s_col = tau_s ? d_in : nullptr;
+    a.mu_s_col = mu_s ? d_in + n : nullptr;
+    a.albedo_col = albedo ? d_in + 2 * n : nullptr;
+    a.solar_irr = s->d_solar_col;
+    a.r_total = d_rt;
+    a.cloud_tau = cloud_from_tau_s ? s->d_cloud_col : nullptr;
+    cudaError_t e = rcm_launch_solar(a, s->stream);
+    if (e == cudaSuccess && solar_irr_out)
+        e = cudaMemcpyAsync(solar_irr_out, s->d_solar_col, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess && r_total_out)
+        e = cudaMemcpyAsync(r_total_out, d_rt, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    cudaFree(d_in);
+    if (d_rt) cudaFree(d_rt);
+    if (e != cudaSuccess) return cuda_fail(s, e, "rcm_set_column_solar");
+    s->launches += 1;
+    s->has_col_solar = true;
+    s->has_col_cloud = cloud_from_tau_s != 0;
+    s->tau_valid = false;
     return RCM_OK;
 }
 
@@ -739,6 +801,8 @@ static int lbl_advance(rcm_solver* s, int nsteps) {
     a.Tlayer = s->d_T; a.Tsurf = s->d_Ts; a.vmr = s->d_vmr; a.rel_hum = s->d_rh; a.Tprev = s->d_Tprev;
     a.time_h = s->d_time; a.sH = s->d_sH; a.sO = s->d_sO; a.dTstat = s->d_dTstat; a.part = s->d_part;
     a.E_down = s->d_Ed; a.E_up = s->d_Eu; a.dE = s->d_dE; a.dt = s->d_dt;
+    a.solar_col = s->has_col_solar ? s->d_solar_col : nullptr;
+    a.cloud_col = s->has_col_cloud ? s->d_cloud_col : nullptr;
     for (int k = 0; k < nsteps; ++k) {
         a.step_index = s->step_index + k;
         a.diag = s->d_diag + (size_t)k * s->ncol * 4;

@@ -225,6 +225,8 @@ struct Smem {
     double* Ts;       // [C]
     double* invTs;    // [C]
     double* dt;       // [C]
+    double* solar;    // [C] absorbed solar irradiance of the column
+    double* cloudc;   // [C] grey-cloud tau of the column
     double* Ed;       // [21][C]   natural level order
     double* Eu;       // [21][C]
     double* dE;       // [20][C]   natural layer order
@@ -236,7 +238,7 @@ struct Smem {
     int* outside;     // [20] then [10]: some column of the tile needs a row beyond the two candidates
     static constexpr size_t ep_stride = STAGE ? (size_t)ROWBUF : PART * sizeof(double);
     static size_t bytes(int nactive) {
-        return ((size_t)EXP_TAB * EXP_REP + 3 * (size_t)NLAY * C + (size_t)nactive * NLAY * C + 3 * (size_t)C +
+        return ((size_t)EXP_TAB * EXP_REP + 3 * (size_t)NLAY * C + (size_t)nactive * NLAY * C + 5 * (size_t)C +
                 (STAGE ? 0 : 2 * (size_t)NLEV * C + (size_t)NLAY * C)) * sizeof(double) + EP_BYTES +
                (2 * (size_t)NLAY * C + (NCAND + 3) * NLAY + HALF + 2) * sizeof(int);
     }
@@ -251,6 +253,8 @@ struct Smem {
         Ts = p;      p += C;
         invTs = p;   p += C;
         dt = p;      p += C;
+        solar = p;   p += C;
+        cloudc = p;  p += C;
         if (STAGE) {  // tails of the row buffers (free while the partials are reduced and until the next request)
             Ed = reinterpret_cast<double*>(ep + 0 * ep_stride) + PART;
             Eu = reinterpret_cast<double*>(ep + 1 * ep_stride) + PART;
@@ -337,14 +341,19 @@ __global__ void __launch_bounds__(NT, min_ctas(NT)) rcm_step_kernel(const StepAr
             s.vmr[(sp * NLAY + prow(l)) * C + cc] =
                 (cc < ncl) ? a.vmr[((size_t)(col0 + cc) * nact + sp) * NLAY + l] : 0.0;
         }
-        if (tid < C) s.Ts[tid] = (tid < ncl) ? a.Tsurf[col0 + tid] : 250.0;
+        if (tid < C) {
+            const int cc = col0 + (tid < ncl ? tid : 0);
+            s.Ts[tid] = (tid < ncl) ? a.Tsurf[col0 + tid] : 250.0;
+            s.solar[tid] = a.solar_col ? a.solar_col[cc] : cst.solar_irr;
+            s.cloudc[tid] = a.cloud_col ? a.cloud_col[cc] : cst.cloud_tau;
+        }
         __syncthreads();
 
         // K1 for one owned layer j (local index) and wavelength w: bilinear (p,T) interpolation of the cross
         // sections in the reference's operation order, no FMA contraction -> tau is bit-identical to
         // read_tau's for identical inputs.  The four bilinear coefficients c0, cT, cP, cPT
         // (repwvl_thermal.cpp:235-238) depend on the table alone and are precomputed per cell (rcm_coef_kernel).
-        auto tau_from = [&](int j, const double2* cf) -> double {
+        auto tau_from = [&](int j, const double2* cf, double cl) -> double {
             const int r = h * HALF + j;
             const double dT = s.delT[sb + j * C], dP = cst.delP[r];
             double acc = 0.0;
@@ -359,26 +368,26 @@ __global__ void __launch_bounds__(NT, min_ctas(NT)) rcm_step_kernel(const StepAr
                 acc = __dadd_rn(acc, __dmul_rn(v, s.vmr[k * NLAY * C + sb + j * C]));
             }
             acc = __dmul_rn(acc, cst.numDens[r]);
-            if (cst.cloud_row == r) acc = __dadd_rn(acc, cst.cloud_tau);  // main.cpp:270
+            if (cst.cloud_row == r) acc = __dadd_rn(acc, cl);  // main.cpp:270, cl: the column's cloud tau
             return acc;
         };
         // ... with the coefficients read from the table in global memory
-        auto tau_cell = [&](int j, int w) -> double {
+        auto tau_cell = [&](int j, int w, double cl) -> double {
             const int cell = cst.ipcell[h * HALF + j] + s.it[sb + j * C];
-            return tau_from(j, reinterpret_cast<const double2*>(a.coef) + (size_t)(cell * nwvl + w) * 2 * nact);
+            return tau_from(j, reinterpret_cast<const double2*>(a.coef) + (size_t)(cell * nwvl + w) * 2 * nact, cl);
         };
         // ... or from the rows staged in this warp's buffer
-        auto tau_staged = [&](int j) -> double {
-            return tau_from(j, reinterpret_cast<const double2*>(rows + s.rowsel[sb + j * C]));
+        auto tau_staged = [&](int j, double cl) -> double {
+            return tau_from(j, reinterpret_cast<const double2*>(rows + s.rowsel[sb + j * C]), cl);
         };
         // tau of owned layer j at wavelength w as the transmissions will use it (w is clamped by the caller)
-        auto tau_use = [&](int j, int w) -> double {
+        auto tau_use = [&](int j, int w, double cl) -> double {
             double v;
             if (MODE == MODE_RT) {
                 const int l = h ? (NLAY - 1 - j) : j;
                 v = live ? a.tau_io[((size_t)(col0 + c) * nwvl + w) * NLAY + l] : 0.0;
             } else {
-                v = tau_cell(j, w);
+                v = tau_cell(j, w, cl);
             }
             if (!CLAMPK) v = fmin(v, a.tau_clamp);  // exp(-tau_clamp/mu) ~ 1e-100: same fluxes, see exp_scaled
             return v;
@@ -471,10 +480,11 @@ __global__ void __launch_bounds__(NT, min_ctas(NT)) rcm_step_kernel(const StepAr
                             a.lowpos_t[(size_t)(col0 + cc) * NLAY + (NLAY - 1 - l)] = s.it[prow(l) * C + cc];
                     }
                 }
+                const double cl = s.cloudc[c];
                 for (int w = g; w < nwvl; w += G) {
 #pragma unroll
                     for (int j = 0; j < HALF; ++j) {
-                        const double t = tau_cell(j, w);
+                        const double t = tau_cell(j, w, cl);
                         const int l = h ? (NLAY - 1 - j) : j;
                         if (live) a.tau_io[((size_t)(col0 + c) * nwvl + w) * NLAY + l] = t;
                     }
@@ -499,18 +509,19 @@ __global__ void __launch_bounds__(NT, min_ctas(NT)) rcm_step_kernel(const StepAr
                 const bool real = w_any < nwvl;
                 const int w = real ? w_any : nwvl - 1;
                 double tau[HALF], Bo[HALF];
+                const double cl = (MODE == MODE_RT) ? 0.0 : s.cloudc[c];  // read per item: not live across the angle loop
                 if (stage) wait_rows();  // the rows of this wavelength were requested one wavelength ago
                 // two straight-line versions of K1 (a branch per layer would cut the block the loads are scheduled in);
                 // a tile where some column needs a row beyond the two candidates takes the global one for every layer
                 if (stage && !s.outside[NLAY]) {
 #pragma unroll
                     for (int j = 0; j < HALF; ++j) {
-                        const double v = tau_staged(j);
+                        const double v = tau_staged(j, cl);
                         tau[j] = CLAMPK ? v : fmin(v, a.tau_clamp);
                     }
                 } else {
 #pragma unroll
-                    for (int j = 0; j < HALF; ++j) tau[j] = tau_use(j, w);
+                    for (int j = 0; j < HALF; ++j) tau[j] = tau_use(j, w, cl);
                 }
                 // K1 has consumed the buffer: the rows of the NEXT wavelength travel while this one's angles run
                 // (nothing is requested after the last one: the buffer then carries the flux partials)
@@ -554,7 +565,7 @@ __global__ void __launch_bounds__(NT, min_ctas(NT)) rcm_step_kernel(const StepAr
             for (int i = tid; i < NLAY * C; i += NT) {
                 const int l = i / C, cc = i % C;
                 double d = s.Ed[l * C + cc] - s.Ed[(l + 1) * C + cc] + s.Eu[(l + 1) * C + cc] - s.Eu[l * C + cc];
-                if (l == NLAY - 1) d += cst.solar_irr + s.Ed[NLAY * C + cc] - s.Eu[NLAY * C + cc];
+                if (l == NLAY - 1) d += s.solar[cc] + s.Ed[NLAY * C + cc] - s.Eu[NLAY * C + cc];
                 s.dE[i] = d;
             }
             __syncthreads();
@@ -583,7 +594,7 @@ __global__ void __launch_bounds__(NT, min_ctas(NT)) rcm_step_kernel(const StepAr
                     a.time_h[col] += (float)dt / 3600;  // main.cpp:581
                     if (a.diag) {
                         double* dg = a.diag + ((size_t)step * a.diag_ncol + col) * 4;
-                        dg[0] = cst.solar_irr - s.Eu[tid];
+                        dg[0] = s.solar[tid] - s.Eu[tid];
                         dg[1] = dT_stat;
                         dg[2] = mabs;
                         dg[3] = dt;
@@ -909,6 +920,7 @@ __global__ void __launch_bounds__(NT, 384 / NT) rcm_lbl_rt_kernel(const LblArgs 
     double* s_sH = p;  p += NLAY * C;
     double* s_sO = p;  p += NLAY * C;
     double* s_Ts = p;  p += C;
+    double* s_cl = p;  p += C;
     double* s_Ep = p;  // [21][GC]
     const int tid = threadIdx.x, lane = tid & 31;
     const int h = tid & 1, q = tid >> 1, c = q % C, g = q / C;
@@ -925,7 +937,10 @@ __global__ void __launch_bounds__(NT, 384 / NT) rcm_lbl_rt_kernel(const LblArgs 
         s_sH[r] = ok ? a.sH[gi] : 1.0;
         s_sO[r] = ok ? a.sO[gi] : 1.0;
     }
-    if (tid < C) s_Ts[tid] = (tid < ncl) ? a.Tsurf[col0 + tid] : 250.0;
+    if (tid < C) {
+        s_Ts[tid] = (tid < ncl) ? a.Tsurf[col0 + tid] : 250.0;
+        s_cl[tid] = a.cloud_col ? a.cloud_col[col0 + (tid < ncl ? tid : 0)] : cst.cloud_tau;
+    }
     __syncthreads();
 
     double E1[HALF], E2[HALF], Eu20 = 0.0;
@@ -952,7 +967,7 @@ __global__ void __launch_bounds__(NT, 384 / NT) rcm_lbl_rt_kernel(const LblArgs 
             v = __dadd_rn(v, __dmul_rn(__ldg(t5 + 2 * plane + l), s_sO[sb + j * C]));
             v = __dadd_rn(v, __ldg(t5 + 3 * plane + l));
             v = __dadd_rn(v, __ldg(t5 + 4 * plane + l));
-            if (cst.cloud_row == h * HALF + j) v = __dadd_rn(v, cst.cloud_tau);
+            if (cst.cloud_row == h * HALF + j) v = __dadd_rn(v, s_cl[c]);
             tau[j] = CLAMPK ? v : fmin(v, a.tau_clamp);
             const double B = cplkavg_narrow(lo, hi, whi, wlo, s_T[sb + j * C], tab_lane);
             Bo[j] = real ? B : 0.0;
@@ -999,11 +1014,12 @@ __global__ void __launch_bounds__(128) rcm_lbl_finish_kernel(const LblArgs a) {
             Eu[l] += pp[21 + l];
         }
     }
+    const double solar = a.solar_col ? a.solar_col[col] : cst.solar_irr;
     double dE[NLAY], mx = -1e300, mabs = 0.0;
 #pragma unroll
     for (int l = 0; l < NLAY; ++l) {
         double d = Ed[l] - Ed[l + 1] + Eu[l + 1] - Eu[l];                      // main.cpp:338
-        if (l == NLAY - 1) d += cst.solar_irr + Ed[NLAY] - Eu[NLAY];           // main.cpp:341
+        if (l == NLAY - 1) d += solar + Ed[NLAY] - Eu[NLAY];                   // main.cpp:341
         dE[l] = d;
         if (mx < d) mx = d;
         mabs = fmax(mabs, fabs(d));
@@ -1028,11 +1044,51 @@ __global__ void __launch_bounds__(128) rcm_lbl_finish_kernel(const LblArgs a) {
     }
     if (a.diag) {
         double* dg = a.diag + (size_t)col * 4;
-        dg[0] = cst.solar_irr - Eu[0];
+        dg[0] = solar - Eu[0];
         dg[1] = a.dTstat[col];
         dg[2] = mabs;
         dg[3] = dt;
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// Solar setup per column: doubling_adding + solar_radiative_transfer_setup
+// (main.cpp:214-264) with per-column cloud optical depth, zenith cosine and surface albedo.  One thread per
+// column, the reference's operation order, no FMA contraction (explicit round-to-nearest intrinsics, IEEE
+// division); pow(2, doublings) is an exact power of two, pow(t_dir, 2) the correctly rounded square.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) rcm_solar_kernel(const SolarArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const double tau_s = a.tau_s_col ? a.tau_s_col[i] : a.tau_s;
+    const double mu_s = a.mu_s_col ? a.mu_s_col[i] : a.mu_s;
+    const double albedo = a.albedo_col ? a.albedo_col[i] : a.albedo;
+    auto mul = [](double x, double y) { return __dmul_rn(x, y); };
+    auto add = [](double x, double y) { return __dadd_rn(x, y); };
+    auto sub = [](double x, double y) { return __dsub_rn(x, y); };
+    auto dvd = [](double x, double y) { return __ddiv_rn(x, y); };
+    const double tau = mul(sub(1.0, a.g_asym), tau_s);                       // main.cpp:216
+    const double dtau = dvd(tau, scalbn(1.0, a.doublings));                  // :217
+    const double thin = dvd(dtau, mu_s);
+    double r = mul(0.5, thin), t = sub(1.0, r);                              // :223-224
+    double r_dir = mul(thin, 0.5), s_dir = r_dir, t_dir = sub(1.0, thin);    // :225-227
+    for (int k = 0; k < a.doublings; ++k) {                                  // :232-250
+        const double denom = sub(1.0, mul(r, r));
+        const double r2 = add(r, dvd(mul(mul(r, t), t), denom));
+        const double t2 = dvd(mul(t, t), denom);
+        const double s2 = add(dvd(add(mul(t, s_dir), mul(mul(mul(t_dir, r_dir), r), t)), denom), mul(t_dir, s_dir));
+        const double rd2 = add(dvd(add(mul(mul(t, s_dir), r), mul(mul(t, t_dir), r)), denom), r_dir);
+        t_dir = mul(t_dir, t_dir);
+        s_dir = s2;
+        r_dir = rd2;
+        r = r2;
+        t = t2;
+    }
+    // solar_radiative_transfer_setup, main.cpp:258-260
+    const double r_total = add(r_dir, mul(mul(dvd(add(t_dir, s_dir), sub(1.0, mul(albedo, r))), t), albedo));
+    if (a.r_total) a.r_total[i] = r_total;
+    if (a.solar_irr) a.solar_irr[i] = mul(mul(mul(a.daytime, a.E_0), mu_s), sub(1.0, r_total));
+    if (a.cloud_tau) a.cloud_tau[i] = dvd(tau_s, 2.0);                       // main.cpp:267
 }
 
 __global__ void __launch_bounds__(256) rcm_cplkavg_kernel(int n, const double* lo, const double* hi, const double* t,
@@ -1121,6 +1177,12 @@ cudaError_t rcm_launch_microbench(int which, double* out, const double* tab, lon
     return cudaGetLastError();
 }
 
+cudaError_t rcm_launch_solar(const SolarArgs& a, cudaStream_t st) {
+    if (a.n <= 0) return cudaSuccess;
+    rcm_solar_kernel<<<(a.n + 127) / 128, 128, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
 cudaError_t rcm_launch_cplkavg(int n, const double* lo, const double* hi, const double* t, double* out,
                                const double* exp_tab, int narrow, cudaStream_t st) {
     rcm_cplkavg_kernel<<<148, 256, 0, st>>>(n, lo, hi, t, out, exp_tab, narrow);
@@ -1128,7 +1190,7 @@ cudaError_t rcm_launch_cplkavg(int n, const double* lo, const double* hi, const 
 }
 
 size_t rcm_lbl_smem_bytes(int C, int nthreads) {
-    return ((size_t)EXP_TAB * EXP_REP + (size_t)NLAY * C * 3 + C + (size_t)NLEV * (nthreads / 2)) * sizeof(double);
+    return ((size_t)EXP_TAB * EXP_REP + (size_t)NLAY * C * 3 + 2 * C + (size_t)NLEV * (nthreads / 2)) * sizeof(double);
 }
 
 cudaError_t rcm_launch_lbl_step(const LblArgs& a, cudaStream_t st) {

@@ -76,6 +76,9 @@ struct StepArgs {
     int* lowpos_t;         // [ncol][20] bottom-up (MODE_TAU)
     const double* exp_tab; // [64] 2^(j/64)
     int h2o_slot;          // position of H2O in the active list, -1 if absent
+    // per-column solar forcing / grey-cloud optical depth (rcm_set_column_solar); NULL = the ensemble-wide constants
+    const double* solar_col;  // [ncol] absorbed solar irradiance, W/m2 (main.cpp:255-264 per column)
+    const double* cloud_col;  // [ncol] tau added to the cloud layer (main.cpp:266-274 per column)
 };
 
 // Line-by-line path: arguments of the three per-step kernels.
@@ -94,6 +97,7 @@ struct LblArgs {
     double* sH; double* sO; double* dTstat;  // [ncol][20], [ncol][20], [ncol]
     double* part;                            // [nchunks][ncol][42]
     double* E_down; double* E_up; double* dE; double* dt; double* diag;
+    const double* solar_col; const double* cloud_col;  // as StepArgs
 };
 
 enum { MODE_STEP = 0, MODE_TAU = 1, MODE_RT = 2 };
@@ -110,6 +114,16 @@ cudaError_t rcm_launch_microbench(int which, double* out, const double* tab, lon
                                   cudaStream_t st);
 size_t rcm_lbl_smem_bytes(int C, int nthreads);
 cudaError_t rcm_launch_lbl_step(const LblArgs& a, cudaStream_t st);
+// doubling_adding + solar_radiative_transfer_setup (main.cpp:214-264) for n columns, one thread each.  tau_s / mu_s /
+// albedo: per-column arrays or NULL (then the scalar in sp).  Outputs (any may be NULL): solar_irr, r_total, and
+// cloud_tau = tau_s / 2 (the thermal grey-cloud term of the same cloud, main.cpp:267).
+struct SolarArgs {
+    int n, doublings;
+    double tau_s, mu_s, g_asym, albedo, daytime, E_0;
+    const double* tau_s_col; const double* mu_s_col; const double* albedo_col;
+    double* solar_irr; double* r_total; double* cloud_tau;
+};
+cudaError_t rcm_launch_solar(const SolarArgs& a, cudaStream_t st);
 cudaError_t rcm_launch_cplkavg(int n, const double* lo, const double* hi, const double* t, double* out,
                                const double* exp_tab, int narrow, cudaStream_t st);
 
