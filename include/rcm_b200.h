@@ -206,6 +206,21 @@ int rcm_get_state(rcm_solver* s, double* Tlayer, double* Tsurf, double* h2o, flo
 
 /* One call = one reference loop iteration with HOST buffers in and out (what bench.py's e2e
  * leg times): rcm_update_columns + 1 fused step + download of E_down, E_up, dE, Tlayer, Tsurf. */
+/* Checkpoint / restart: everything the step reads or carries (T, Tsurf, active VMRs, rel_hum, the
+ * previous sorted profile, model time, last dt / fluxes / dE, per-column forcing, step index, pressure grid) in one
+ * flat little-endian file.  A solver with the same table and species_mask that loads it continues bit-identically.
+ * Tables are not stored.  Errors: RCM_ERR_IO, RCM_ERR_FORMAT (not a checkpoint / truncated), RCM_ERR_STATE (other
+ * species_mask or spectral path). */
+int rcm_save_checkpoint(rcm_solver* s, const char* path);
+int rcm_load_checkpoint(rcm_solver* s, const char* path);
+int rcm_column_count(const rcm_solver* s); /* columns currently loaded (rcm_set_columns / rcm_load_checkpoint) */
+/* Batched form of output_conv (main.cpp:102-114): for every column the 20 rows "layer,player,Tlayer,theta,time"
+ * ("%d,%f,%f,%f,%f\n", theta = Tlayer * (1000/player)^(2/7) as t_to_theta, main.cpp:123-127; time in hours).
+ * column_ids != 0 prefixes every row with the column number ("%d,"); with ncol == 1 and column_ids == 0 the rows are
+ * byte-identical to the reference's.  append != 0 appends like the reference's freopen(..., "a"); header != 0 writes
+ * the reference's header line (main.cpp:528) first.  Host only. */
+int rcm_write_profiles(const char* path, int append, int header, int ncol, const double* plevel_hPa,
+                       const double* Tlayer, const float* time_h, int column_ids);
 int rcm_step_host(rcm_solver* s, const double* Tlayer_in, const double* Tsurf_in, const double* vmr_active_in,
                   double* E_down, double* E_up, double* dE, double* Tlayer_out, double* Tsurf_out);
 

@@ -8,8 +8,8 @@ no CPU fallback - every compute call fails loudly when the library or a GPU is m
 """
 from .capi import (RcmError, Solver, Table, StepScalars, default_params, default_solar_params, solar_setup,  # noqa: F401
                    lowerpos, read_atm, init_columns, make_ensemble, make_lbl_tables, write_lbl_asc, ascii_file2xy2D, cplkavg_host, device_count,
-                   library_path, load_library, build_library, DECLARED_SYMBOLS)
+                   write_profiles, SolarParams, library_path, load_library, build_library, DECLARED_SYMBOLS)
 
 __all__ = ["RcmError", "Solver", "Table", "StepScalars", "default_params", "default_solar_params", "solar_setup",
            "lowerpos", "read_atm", "init_columns", "make_ensemble", "make_lbl_tables", "write_lbl_asc", "ascii_file2xy2D", "cplkavg_host", "device_count",
-           "library_path", "load_library", "build_library", "DECLARED_SYMBOLS"]
+           "write_profiles", "SolarParams", "library_path", "load_library", "build_library", "DECLARED_SYMBOLS"]

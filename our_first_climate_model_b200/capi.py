@@ -122,6 +122,15 @@ def solar_setup(sp: SolarParams | None = None) -> dict:
     return dict(zip(["r_dir", "s_dir", "t_dir", "r", "t", "r_total", "solar_irr"], out))
 
 
+def write_profiles(path: str, plevel, Tlayer, time_h, append=False, header=False, column_ids=False):
+    """rcm_write_profiles: the reference's output_conv rows (main.cpp:102-114) for a whole ensemble."""
+    T = _f64(Tlayer).reshape(-1, NLAY)
+    th = np.ascontiguousarray(np.broadcast_to(time_h, (T.shape[0],)), dtype=np.float32)
+    _check(load_library().rcm_write_profiles(path.encode(), C.c_int(int(append)), C.c_int(int(header)),
+                                             C.c_int(T.shape[0]), _p(_f64(plevel, (NLEV,))), _p(T), _p(th),
+                                             C.c_int(int(column_ids))))
+
+
 def lowerpos(nodes, x) -> int:
     a = _f64(nodes)
     return int(load_library().rcm_lowerpos(_p(a), C.c_int(a.size), C.c_double(x)))
@@ -345,6 +354,13 @@ class Solver:
                                          C.c_int(1 if cloud_from_tau_s else 0), _p(out["solar_irr"]),
                                          _p(out["r_total"])), self._h)
         return out
+
+    def save_checkpoint(self, path: str):
+        _check(_lib.rcm_save_checkpoint(self._h, path.encode()), self._h)
+
+    def load_checkpoint(self, path: str):
+        _check(_lib.rcm_load_checkpoint(self._h, path.encode()), self._h)
+        self.ncol = int(_lib.rcm_column_count(self._h))
 
     def update_columns(self, Tlayer=None, Tsurf=None, vmr_active=None):
         a = None if Tlayer is None else _f64(Tlayer, (self.ncol, NLAY))

@@ -360,4 +360,39 @@ int rcm_ascii_file2xy2D(const char* filename, int* nx, int* ny, double** x, doub
 
 void rcm_free(void* p) { std::free(p); }
 
+// Batched output_conv (main.cpp:102-114): see include/rcm_b200.h.
+int rcm_write_profiles(const char* path, int append, int header, int ncol, const double* plevel_hPa,
+                       const double* Tlayer, const float* time_h, int column_ids) {
+    if (!path || ncol < 0 || !plevel_hPa || (ncol > 0 && (!Tlayer || !time_h))) return RCM_ERR_ARG;
+    double player[RCM_NLAYER], conv[RCM_NLAYER];
+    for (int l = 0; l < RCM_NLAYER; ++l) {
+        player[l] = (plevel_hPa[l] + plevel_hPa[l + 1]) / 2.0;   // main.cpp:472
+        conv[l] = std::pow(1000.0 / player[l], 2.0 / 7.0);       // main.cpp:474
+    }
+    FILE* f = std::fopen(path, append ? "a" : "w");
+    if (!f) return RCM_ERR_IO;
+    std::string out;
+    out.reserve(1 << 20);
+    char row[160];
+    bool ok = true;
+    if (header) out += column_ids ? "column,layer,player,Tlayer,theta,time\n" : "layer,player,Tlayer,theta,time\n";
+    for (int c = 0; c < ncol && ok; ++c) {
+        const double* T = Tlayer + (size_t)c * RCM_NLAYER;
+        for (int l = 0; l < RCM_NLAYER; ++l) {
+            const double theta = T[l] * conv[l];  // t_to_theta, main.cpp:125
+            int n = 0;
+            if (column_ids) n = std::snprintf(row, sizeof(row), "%d,", c);
+            n += std::snprintf(row + n, sizeof(row) - n, "%d,%f,%f,%f,%f\n", l, player[l], T[l], theta, (double)time_h[c]);
+            out.append(row, (size_t)n);
+        }
+        if (out.size() > (1u << 20) - 4096) {
+            ok = std::fwrite(out.data(), 1, out.size(), f) == out.size();
+            out.clear();
+        }
+    }
+    if (ok && !out.empty()) ok = std::fwrite(out.data(), 1, out.size(), f) == out.size();
+    ok = (std::fclose(f) == 0) && ok;
+    return ok ? RCM_OK : RCM_ERR_IO;
+}
+
 }  // extern "C"

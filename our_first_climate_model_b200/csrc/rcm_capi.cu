@@ -888,6 +888,124 @@ int rcm_get_state(rcm_solver* s, double* Tlayer, double* Tsurf, double* h2o, flo
     return RCM_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// Checkpoint / restart of an ensemble.  One flat little-endian file:
+//   "RCMCKPT1", header (int64: ncol, nactive, species_mask, step_index, has_col_solar, has_col_cloud, lbl_mode,
+//   reserved), plevel[21], then per column arrays in the order of kCkptArrays below.
+// Everything the step reads or carries is in it, so a solver that loads the same table and this file continues
+// bit-identically (tests/test_gpu_checkpoint.py).  Tables are not stored: they are inputs of the run, not state.
+// ------------------------------------------------------------------------------------------
+namespace {
+struct CkptArray { void* dev; size_t bytes; };
+
+int ckpt_arrays(rcm_solver* s, CkptArray* out, bool col_solar, bool col_cloud) {
+    const size_t n = (size_t)s->ncol, D = sizeof(double);
+    int k = 0;
+    out[k++] = {s->d_T, n * NLAY * D};
+    out[k++] = {s->d_Ts, n * D};
+    out[k++] = {s->d_vmr, n * s->nactive * NLAY * D};
+    out[k++] = {s->d_rh, n * NLAY * D};
+    out[k++] = {s->d_Tprev, n * NLAY * D};
+    out[k++] = {s->d_time, n * sizeof(float)};
+    out[k++] = {s->d_dt, n * D};
+    out[k++] = {s->d_Ed, n * NLEV * D};
+    out[k++] = {s->d_Eu, n * NLEV * D};
+    out[k++] = {s->d_dE, n * NLAY * D};
+    if (col_solar) out[k++] = {s->d_solar_col, n * D};
+    if (col_cloud) out[k++] = {s->d_cloud_col, n * D};
+    return k;
+}
+}  // namespace
+
+int rcm_column_count(const rcm_solver* s) { return s ? s->ncol : 0; }
+
+int rcm_save_checkpoint(rcm_solver* s, const char* path) {
+    if (!s || !path) return RCM_ERR_ARG;
+    if (s->ncol <= 0) return fail(s, RCM_ERR_STATE, "no columns loaded");
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->stream));
+    FILE* f = std::fopen(path, "wb");
+    if (!f) return fail(s, RCM_ERR_IO, std::string("cannot write ") + path);
+    const long long hdr[8] = {s->ncol, s->nactive, (long long)s->p.species_mask, s->step_index, s->has_col_solar ? 1 : 0,
+                              s->has_col_cloud ? 1 : 0, s->lbl_mode ? 1 : 0, 0};
+    bool ok = std::fwrite("RCMCKPT1", 1, 8, f) == 8 && std::fwrite(hdr, sizeof(hdr), 1, f) == 1 &&
+              std::fwrite(s->plevel, sizeof(s->plevel), 1, f) == 1;
+    CkptArray arr[12];
+    const int na = ckpt_arrays(s, arr, s->has_col_solar, s->has_col_cloud);
+    std::vector<char> buf;
+    for (int k = 0; k < na && ok; ++k) {
+        buf.resize(arr[k].bytes);
+        cudaError_t e = cudaMemcpy(buf.data(), arr[k].dev, arr[k].bytes, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) {
+            std::fclose(f);
+            return cuda_fail(s, e, "checkpoint download");
+        }
+        ok = std::fwrite(buf.data(), 1, arr[k].bytes, f) == arr[k].bytes;
+    }
+    ok = (std::fclose(f) == 0) && ok;
+    return ok ? RCM_OK : fail(s, RCM_ERR_IO, std::string("short write to ") + path);
+}
+
+int rcm_load_checkpoint(rcm_solver* s, const char* path) {
+    if (!s || !path) return RCM_ERR_ARG;
+    CU(cudaSetDevice(s->device));
+    FILE* f = std::fopen(path, "rb");
+    if (!f) return fail(s, RCM_ERR_IO, std::string("cannot read ") + path);
+    char magic[8];
+    long long hdr[8];
+    double plevel[RCM_NLEVEL];
+    if (std::fread(magic, 1, 8, f) != 8 || std::memcmp(magic, "RCMCKPT1", 8) != 0 || std::fread(hdr, sizeof(hdr), 1, f) != 1 ||
+        std::fread(plevel, sizeof(plevel), 1, f) != 1 || hdr[0] <= 0 || hdr[0] > (1LL << 30)) {
+        std::fclose(f);
+        return fail(s, RCM_ERR_FORMAT, std::string(path) + " is not a checkpoint of this solver");
+    }
+    set_active_species(s);
+    if ((unsigned)hdr[2] != s->p.species_mask || (int)hdr[1] != s->nactive) {
+        std::fclose(f);
+        return fail(s, RCM_ERR_STATE, "checkpoint was written with another species_mask");
+    }
+    if ((hdr[6] != 0) != s->lbl_mode) {
+        std::fclose(f);
+        return fail(s, RCM_ERR_STATE, "checkpoint belongs to the other spectral path (repwvl / line-by-line)");
+    }
+    int st = ensure_columns(s, (int)hdr[0]);
+    if (st != RCM_OK) {
+        std::fclose(f);
+        return st;
+    }
+    s->ncol = (int)hdr[0];
+    if ((hdr[4] || hdr[5]) && !s->d_solar_col) {
+        CU(dalloc(s->d_solar_col, (size_t)s->cap));
+        CU(dalloc(s->d_cloud_col, (size_t)s->cap));
+    }
+    CkptArray arr[12];
+    const int na = ckpt_arrays(s, arr, hdr[4] != 0, hdr[5] != 0);
+    std::vector<char> buf;
+    for (int k = 0; k < na; ++k) {
+        buf.resize(arr[k].bytes);
+        if (std::fread(buf.data(), 1, arr[k].bytes, f) != arr[k].bytes) {
+            std::fclose(f);
+            s->ncol = 0;
+            return fail(s, RCM_ERR_FORMAT, std::string(path) + " is truncated");
+        }
+        cudaError_t e = cudaMemcpy(arr[k].dev, buf.data(), arr[k].bytes, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            std::fclose(f);
+            s->ncol = 0;
+            return cuda_fail(s, e, "checkpoint upload");
+        }
+    }
+    std::fclose(f);
+    std::memcpy(s->plevel, plevel, sizeof(plevel));
+    s->has_plevel = true;
+    s->const_dirty = true;
+    s->step_index = (long)hdr[3];
+    s->has_col_solar = hdr[4] != 0;
+    s->has_col_cloud = hdr[5] != 0;
+    s->tau_valid = false;
+    return RCM_OK;
+}
+
 // Host buffers in, one step, host buffers out.  For big repwvl ensembles the columns are cut into chunks that
 // travel through three internal streams: while chunk k is stepped, chunk k+1 is on its way up and chunk k-1 on
 // its way down (separate copy engines), so the call costs about one step plus one chunk of copies instead of

@@ -168,3 +168,35 @@ def test_cplkavg_host_matches_reference_samples(rcm, golden_misc):
     got = np.array([rcm.cplkavg_host(a, b, t)[0] for a, b, t in zip(m["cpl_lo"], m["cpl_hi"], m["cpl_T"])])
     assert np.array_equal(got, m["cpl_val"])
     assert rcm.cplkavg_host(500.0, 400.0, 300.0)[1] == 1
+
+
+def test_write_profiles_reproduces_reference_output_rows(rcm, golden, tmp_path):
+    """rcm_write_profiles = output_conv (main.cpp:102-114) batched: the t=0 rows of the reference's committed output.txt
+    (/root/reference/output.txt:7-27) byte for byte; append / header / column-id forms."""
+    rows = """0,25.000000,221.393000,635.177801 1,75.000000,221.393000,464.060873 2,125.000000,221.393000,401.041758
+    3,175.000000,221.393000,364.282852 4,225.000000,221.393000,339.042853 5,275.000000,225.299500,325.799855
+    6,325.000000,232.616500,320.702550 7,375.000000,239.063000,316.386335 8,425.000000,244.842000,312.651495
+    9,475.000000,250.091000,309.365099 10,525.000000,254.908000,306.434706 11,575.000000,259.365500,303.793542
+    12,625.000000,263.518000,301.391001 13,675.000000,267.409000,299.189516 14,725.000000,271.073000,297.159548
+    15,775.000000,274.537000,295.276557 16,825.000000,277.824000,293.521596 17,875.000000,280.953500,291.879487
+    18,925.000000,283.941500,290.337186 19,975.000000,286.801000,288.883142""".split()
+    st = rcm.init_columns(golden["plevel"], golden["Tlevel"][:1], golden["vmr_ppm_level"][:1])
+    path = str(tmp_path / "output.txt")
+    rcm.write_profiles(path, golden["plevel"], st["Tlayer"], 0.0, header=True)
+    want = "layer,player,Tlayer,theta,time\n" + "".join(r + ",0.000000\n" for r in rows)
+    assert open(path).read() == want
+    rcm.write_profiles(path, golden["plevel"], st["Tlayer"], np.float32(3.668250), append=True)   # dt/3600 of step 0
+    txt = open(path).read()
+    assert txt.startswith(want) and txt.endswith("19,975.000000,286.801000,288.883142,3.668250\n") and txt.count("\n") == 41
+    # an ensemble: 3000 columns x 20 rows with column ids, large enough to cross the writer's flush threshold
+    n = 3000
+    T = np.tile(st["Tlayer"], (n, 1)) + np.arange(n)[:, None] * 1e-3
+    rcm.write_profiles(path, golden["plevel"], T, np.arange(n, dtype=np.float32), header=True, column_ids=True)
+    lines = open(path).read().splitlines()
+    assert lines[0] == "column,layer,player,Tlayer,theta,time" and len(lines) == 1 + 20 * n
+    c, l = 2999, 7
+    player = (golden["plevel"][l] + golden["plevel"][l + 1]) / 2
+    conv = (1000.0 / player) ** (2.0 / 7.0)
+    assert lines[1 + 20 * c + l] == "%d,%d,%f,%f,%f,%f" % (c, l, player, T[c, l], T[c, l] * conv, float(c))
+    with pytest.raises(rcm.RcmError):
+        rcm.write_profiles(str(tmp_path / "no_such_dir" / "x.txt"), golden["plevel"], st["Tlayer"], 0.0)
