@@ -143,7 +143,7 @@ void build_angles(rcm_solver* s) {
             d.cmu[slot] = 2 * M_PI * mu * dmu;
             sum += d.cmu[slot];
             if (m == 0) {
-                d.neg_inv_mu_l2e[ic] = (-1.0 / mu) * 184.66496523378733;  // times 128/ln2, see exp_scaled
+                d.neg_inv_mu_l2e[ic] = (-1.0 / mu) * EXP_L2E;  // times EXP_TAB/ln2, see exp_scaled
                 x_max = std::max(x_max, 1.0 / mu);
             }
             x_min = std::min(x_min, 1.0 / mu);
@@ -152,10 +152,13 @@ void build_angles(rcm_solver* s) {
     d.nslot = slot;
     d.csum = sum;
     {
-        // h(f) with exp(f c) - 1 = f h(f), c = ln2/128, |f| <= 1/2: Taylor to f^5 with the f^5 term economised
-        // (f^5 ~ 0.3125 f^3 - 0.01953125 f on [-1/2, 1/2], Chebyshev): max relative error 7.6e-17
-        const double ec[4] = {0x1.62e42fefa3685p-8, 0x1.ebfbdff82c58fp-17, 0x1.c6b09b1799fcbp-26, 0x1.3b2ab6fba4e77p-35};
-        for (int k = 0; k < 4; ++k) d.expc[k] = ec[k];
+        // h(f) with exp(f c) - 1 = f h(f), c = ln2/EXP_TAB, |f| <= 1/2.
+        // 128 entries: Taylor to f^5 with the f^5 term economised (f^5 ~ 0.3125 f^3 - 0.01953125 f on [-1/2, 1/2],
+        // Chebyshev), degree 3 in h, max relative error 7.6e-17.
+        // 1024 entries: Taylor to f^4 with the f^4 term economised (f^3 ~ 0.1875 f in h), degree 2 in h, 1.4e-16.
+        const double ec7[4] = {0x1.62e42fefa3685p-8, 0x1.ebfbdff82c58fp-17, 0x1.c6b09b1799fcbp-26, 0x1.3b2ab6fba4e77p-35};
+        const double ec10[4] = {0x1.62e42fefa39efp-11, 0x1.ebfbe033445b4p-23, 0x1.c6b08d704a0c0p-35, 0.0};
+        for (int k = 0; k < 4; ++k) d.expc[k] = (EXP_LOG2 == 7) ? ec7[k] : ec10[k];
     }
     // exp_scaled needs |tau/mu|/ln2 <= 1000 for every slot evaluated with exp.  Clamping tau once per layer
     // guarantees that for free - provided the clamped transmission is still zero for every use

@@ -12,8 +12,18 @@ constexpr int MAX_ANGLE = 64;
 constexpr int MAX_TPERT = 16;
 constexpr int HALF = NLAY / 2;     // layers owned by each lane of a pair
 constexpr int RCM_LBL_C = 16, RCM_LBL_NT = 128;  // tile shape of the LBL radiative-transfer kernel
-constexpr int EXP_LOG2 = 7, EXP_TAB = 1 << EXP_LOG2;  // entries of the 2^(j/128) table used by the solver's exp
-constexpr int EXP_REP = 8;         // copies of every entry side by side, lane l reads copy l & 7 (see exp_scaled)
+// The solver's exp (exp_scaled): table 2^(j/EXP_TAB) in shared memory, EXP_REP copies of every entry side by side
+// (lane l reads copy l & (EXP_REP-1)), Horner polynomial of degree EXP_DEG.  Two 8 KB configurations:
+//   RCM_EXP_LOG2 = 10: 1024 entries, one copy, degree 2 (7 FP64 instructions per exp, approximation error 1.4e-16)
+//   RCM_EXP_LOG2 = 7:   128 entries, eight copies, degree 3 (8 FP64 instructions, 7.6e-17)
+#ifndef RCM_EXP_LOG2
+#define RCM_EXP_LOG2 10
+#endif
+constexpr int EXP_LOG2 = RCM_EXP_LOG2, EXP_TAB = 1 << EXP_LOG2;
+constexpr int EXP_REP = (EXP_LOG2 == 7) ? 8 : 1;
+constexpr int EXP_DEG = (EXP_LOG2 == 7) ? 3 : 2;
+static_assert(EXP_LOG2 == 7 || EXP_LOG2 == 10, "exp table configurations: 128 x 8 copies or 1024 x 1");
+constexpr double EXP_L2E = EXP_TAB * 1.4426950408889634;  // EXP_TAB / ln 2: argument scaling of exp_scaled
 
 // Everything that is uniform over the ensemble.  Lives in __constant__ memory.
 struct DevConst {
