@@ -206,7 +206,7 @@ int refresh_const(rcm_solver* s) {
             const double midP = (P[k + 1] + P[k]) / 2;
             const long ip = rcm_lowerpos_impl(s->p_grid.data(), (int)s->p_grid.size(), midP);
             d.ip[l] = (int)ip;
-            d.ipcell[r] = (int)ip * (d.n_tpert - 1);
+            d.ipcell[r] = r * (d.n_tpert - 1);  // first cell of the layer's block in the per-layer coefficient table
             d.delP[r] = (midP - s->p_grid[ip]) / (s->p_grid[ip + 1] - s->p_grid[ip]);
             d.numDens[r] = (P[k] - P[k + 1]) * avog / molMassAir / earthAccel;
             d.tref_ip[r] = s->t_ref[ip];
@@ -220,9 +220,9 @@ int refresh_const(rcm_solver* s) {
     }
     cudaError_t e = rcm_upload_const(d);
     if (e != cudaSuccess) return cuda_fail(s, e, "upload constants");
-    if (s->has_table && s->coef_dirty) {
-        // bilinear coefficients of the active species: coef[cell][wvl][k][4]
-        const size_t n = (size_t)(d.n_p - 1) * (d.n_tpert - 1) * d.nwvl * s->nactive * 4;
+    if (s->has_table && s->has_plevel && s->coef_dirty) {
+        // bilinear coefficients of the active species per layer: coef[layer row][t interval][wvl][k][4]
+        const size_t n = (size_t)RCM_NLAYER * (d.n_tpert - 1) * d.nwvl * s->nactive * 4;
         CU(dalloc(s->d_coef, n));
         CU(dalloc(s->d_species, (size_t)RCM_NSPECIES));
         CU(cudaMemcpyAsync(s->d_species, s->species, sizeof(s->species), cudaMemcpyHostToDevice, s->stream));
@@ -620,6 +620,7 @@ int rcm_set_columns(rcm_solver* s, int ncol, const double* plevel_hPa, const dou
     int st = ensure_columns(s, ncol);
     if (st != RCM_OK) return st;
     s->ncol = ncol;
+    if (!s->has_plevel || std::memcmp(s->plevel, plevel_hPa, sizeof(s->plevel)) != 0) s->coef_dirty = true;  // per-layer table
     std::memcpy(s->plevel, plevel_hPa, sizeof(s->plevel));
     s->has_plevel = true;
     s->const_dirty = true;
@@ -999,6 +1000,7 @@ int rcm_load_checkpoint(rcm_solver* s, const char* path) {
         }
     }
     std::fclose(f);
+    if (!s->has_plevel || std::memcmp(s->plevel, plevel, sizeof(plevel)) != 0) s->coef_dirty = true;
     std::memcpy(s->plevel, plevel, sizeof(plevel));
     s->has_plevel = true;
     s->const_dirty = true;

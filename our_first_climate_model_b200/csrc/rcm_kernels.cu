@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(NT, min_ctas(NT)) rcm_step_kernel(const StepAr
                 // two 128-bit loads (one 256-bit LDG.E.ENL2.256 was measured 8% slower for the whole step)
                 const double2 c0T = cf[2 * k], cPPT = cf[2 * k + 1];
                 double v = __dadd_rn(c0T.x, __dmul_rn(c0T.y, dT));
-                v = __dadd_rn(v, __dmul_rn(cPPT.x, dP));
+                v = __dadd_rn(v, cPPT.x);  // cP * delP of this layer, rounded once when the table was built
                 v = __dadd_rn(v, __dmul_rn(__dmul_rn(cPPT.y, dT), dP));
                 acc = __dadd_rn(acc, __dmul_rn(v, s.vmr[k * NLAY * C + sb + j * C]));
             }
@@ -631,18 +631,22 @@ __global__ void __launch_bounds__(NT, min_ctas(NT)) rcm_step_kernel(const StepAr
     }
 }
 
-// Bilinear coefficients per table cell and active species, in the reference's operation order
-// (repwvl_thermal.cpp:235-238):  coef[(ip*(nt-1)+it)][w][k] = {c0, cT, cP, cPT}.
+// Bilinear coefficients per LAYER, temperature interval and active species, in the reference's operation order
+// (repwvl_thermal.cpp:235-238):  coef[(r*(nt-1)+it)][w][k] = {c0, cT, cP * delP_r, cPT}, r = pair-order layer row.
+// The layer's pressure interval ip and its weight delP come from the shared pressure grid (constant bank), so the
+// product cP * delP - one rounding in the reference too - is taken here once instead of once per column and step.
 // src is the file-order table xsec[it][species][w][ip].
 __global__ void rcm_coef_kernel(const double* __restrict__ src, double* __restrict__ dst, int nt, int ns, int nw,
                                 int np, int nact, const int* __restrict__ species) {
-    const size_t n = (size_t)(np - 1) * (nt - 1) * nw * nact;
+    const size_t n = (size_t)NLAY * (nt - 1) * nw * nact;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         size_t r = i;
         const int k = r % nact; r /= nact;
         const int w = r % nw; r /= nw;
         const int it = r % (nt - 1); r /= (nt - 1);
-        const int ip = (int)r;
+        const int row = (int)r;                             // pair-order layer row
+        const int l = row < HALF ? row : 29 - row;          // top-down layer
+        const int ip = cst.ip[l];
         const int sp = species[k];
         auto X = [&](int b, int cc) { return src[(((size_t)b * ns + sp) * nw + w) * np + cc]; };
         const double c0 = X(it, ip);
@@ -651,7 +655,7 @@ __global__ void rcm_coef_kernel(const double* __restrict__ src, double* __restri
         const double cPT = __dsub_rn(__dsub_rn(__dsub_rn(X(it + 1, ip + 1), cP), cT), c0);
         dst[4 * i + 0] = c0;
         dst[4 * i + 1] = cT;
-        dst[4 * i + 2] = cP;
+        dst[4 * i + 2] = __dmul_rn(cP, cst.delP[row]);
         dst[4 * i + 3] = cPT;
     }
 }
