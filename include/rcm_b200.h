@@ -124,6 +124,10 @@ int rcm_set_params(rcm_solver* s, const rcm_params* p);
  * mu, mu/3, mu/9 so that two thirds of the transmissions need an exp and the rest are cubes
  * of the previous ones (same mu values, different summation order, ~1e-15 relative). */
 #define RCM_OPT_ANGLE_CUBES 0
+/* RCM_OPT_ANGLE_PAIRS (default 1, needs the cubes): two chain heads whose node numbers satisfy 3a = 5b, 5a = 7b or
+ * 3a = 7b take their transmissions as powers of ONE exp at a virtual node (30 angles: 4 of the 20 exp's per layer
+ * and wavelength become 3-4 multiplications; same mu values, ~1e-14 relative). */
+#define RCM_OPT_ANGLE_PAIRS 4
 int rcm_set_option(rcm_solver* s, int option, int value);
 /* cudaStream_t to launch on (NULL = the solver's own stream). */
 int rcm_set_stream(rcm_solver* s, void* cuda_stream);

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -22,6 +23,7 @@ struct rcm_solver {
     DevConst dc{};
     bool const_dirty = true;
     int opt_angle_cubes = 1;
+    int opt_angle_pairs = 1;   // chain heads that share a virtual root take it from one exp (needs opt_angle_cubes)
     int opt_config = 0;        // 0: planned (plan_parts); k > 0: force kShapes[k-1] for the whole ensemble
         // prepare the next wavelength inside the angle loop (0: separate phase)
     int opt_stage_rows = 1;    // K1 reads its table rows from shared memory, staged one wavelength ahead
@@ -111,6 +113,8 @@ void build_angles(rcm_solver* s) {
     const double dmu = 1.0 / (double)na;
     d.nangle = na;
     std::vector<std::vector<int>> chains;  // node indices, head first
+    struct PairUnit { int type; double inv_mu_root; std::vector<int> a, b; };
+    std::vector<PairUnit> pairs;
     if (s->opt_angle_cubes) {
         std::vector<char> used(na, 0);
         for (int i = na - 1; i >= 0; --i) {
@@ -122,6 +126,45 @@ void build_angles(rcm_solver* s) {
                 if (n % 3 != 0) break;
             }
             chains.push_back(ch);
+        }
+        if (s->opt_angle_pairs) {
+            // Heads a > b with pa*a == pb*b, (pa,pb) in {(3,5),(5,7),(3,7)}: a maximum matching over these few
+            // candidates by exhaustive search (30 angles: 6 candidate edges, 4 disjoint pairs).
+            struct Edge { int ca, cb, type, R; };
+            std::vector<Edge> edges;
+            const int pa_[3] = {3, 5, 3}, pb_[3] = {5, 7, 7};
+            for (size_t x = 0; x < chains.size(); ++x)
+                for (size_t y = 0; y < chains.size(); ++y) {
+                    const int a = 2 * chains[x][0] + 1, b = 2 * chains[y][0] + 1;
+                    for (int t = 0; t < 3; ++t)
+                        if (a > b && pa_[t] * a == pb_[t] * b) edges.push_back({(int)x, (int)y, t, pa_[t] * a});
+                }
+            std::vector<int> best, cur;
+            std::vector<char> taken(chains.size(), 0);
+            std::function<void(size_t)> rec = [&](size_t e) {
+                if (cur.size() > best.size()) best = cur;
+                if (e >= edges.size() || cur.size() + (edges.size() - e) <= best.size() || edges.size() > 24) return;
+                if (!taken[edges[e].ca] && !taken[edges[e].cb]) {
+                    taken[edges[e].ca] = taken[edges[e].cb] = 1;
+                    cur.push_back((int)e);
+                    rec(e + 1);
+                    cur.pop_back();
+                    taken[edges[e].ca] = taken[edges[e].cb] = 0;
+                }
+                rec(e + 1);
+            };
+            rec(0);
+            if (best.size() > (size_t)MAX_PAIR) best.resize(MAX_PAIR);
+            std::vector<char> gone(chains.size(), 0);
+            for (int e : best) {
+                const Edge& ed = edges[e];
+                pairs.push_back({ed.type, 2.0 * na / (double)ed.R, chains[ed.ca], chains[ed.cb]});
+                gone[ed.ca] = gone[ed.cb] = 1;
+            }
+            std::vector<std::vector<int>> rest;
+            for (size_t x = 0; x < chains.size(); ++x)
+                if (!gone[x]) rest.push_back(chains[x]);
+            chains.swap(rest);
         }
     } else {
         for (int i = 0; i < na; ++i) chains.push_back({i});
@@ -135,11 +178,28 @@ void build_angles(rcm_solver* s) {
         d.neg_inv_mu_l2e[a] = 0.0;
         d.cmu[a] = 0.0;
     }
+    auto node_mu = [&](int i) { return dmu / 2.0 + dmu * (double)i; };  // main.cpp:482
+    d.npair = (int)pairs.size();
+    for (int p = 0; p <= MAX_PAIR; ++p) d.pair_nim[p] = 0.0;
+    for (int p = 0; p < d.npair; ++p) {
+        d.pair_type[p] = pairs[p].type;
+        d.pair_lenA[p] = (int)pairs[p].a.size();
+        d.pair_lenB[p] = (int)pairs[p].b.size();
+        d.pair_nim[p] = -pairs[p].inv_mu_root * EXP_L2E;
+        x_max = std::max(x_max, pairs[p].inv_mu_root);
+        for (const std::vector<int>* ch : {&pairs[p].a, &pairs[p].b})
+            for (int i : *ch) {
+                const double mu = node_mu(i);
+                d.cmu[slot] = 2 * M_PI * mu * dmu;
+                sum += d.cmu[slot++];
+                x_min = std::min(x_min, 1.0 / mu);
+            }
+    }
     for (int ic = 0; ic < d.nchain; ++ic) {
         d.chain_len[ic] = (int)chains[ic].size();
         for (size_t m = 0; m < chains[ic].size(); ++m, ++slot) {
             if (chains[ic][m] < 0) continue;
-            const double mu = dmu / 2.0 + dmu * (double)chains[ic][m];  // main.cpp:482
+            const double mu = node_mu(chains[ic][m]);
             d.cmu[slot] = 2 * M_PI * mu * dmu;
             sum += d.cmu[slot];
             if (m == 0) {
@@ -149,6 +209,7 @@ void build_angles(rcm_solver* s) {
             x_min = std::min(x_min, 1.0 / mu);
         }
     }
+    d.pair_nim[d.npair] = d.neg_inv_mu_l2e[0];  // the last pair unit evaluates the first chain's head
     d.nslot = slot;
     d.csum = sum;
     {
@@ -492,6 +553,11 @@ int rcm_set_option(rcm_solver* s, int option, int value) {
     }
     if (option == 3) {
         s->opt_stage_rows = value ? 1 : 0;
+        return RCM_OK;
+    }
+    if (option == 4) {
+        s->opt_angle_pairs = value ? 1 : 0;
+        s->const_dirty = true;
         return RCM_OK;
     }
     return fail(s, RCM_ERR_ARG, "unknown option");

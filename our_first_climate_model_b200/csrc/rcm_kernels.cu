@@ -163,32 +163,61 @@ __device__ __forceinline__ void sweep_item(const double (&tau)[HALF], const doub
     };
     // One chain of angles mu, mu/3, mu/9, ...: the head's transmissions tc were produced during the previous
     // chain; every further level is the cube of the one before (in place).  While the last level is swept,
-    // the transmissions of the NEXT chain's head are evaluated into tn (ten independent exp's that fill
-    // the issue slots the two dependent recurrences leave empty).
+    // the transmissions of the NEXT unit's head (or virtual root) are evaluated into tn (ten independent exp's that
+    // fill the issue slots the two dependent recurrences leave empty).
     int slot = 0;
-    auto chain = [&](double (&tc)[HALF], double (&tn)[HALF], int ic) {
-        const int len = cst.chain_len[ic];
+    auto chain = [&](double (&tc)[HALF], double (&tn)[HALF], int len, double nim) {
 #pragma unroll 1
         for (int k = 1; k < len; ++k) {
             sweep(tc, cst.cmu[slot++]);
 #pragma unroll
             for (int j = 0; j < HALF; ++j) tc[j] = tc[j] * tc[j] * tc[j];
         }
-        const double nim = cst.neg_inv_mu_l2e[ic + 1];
 #pragma unroll
         for (int j = 0; j < HALF; ++j) tn[j] = exp_scaled<CLAMPK>(tau[j], nim, tab_lane);
         sweep(tc, cst.cmu[slot++]);
     };
     const int nchain = cst.nchain;  // even (a zero-weight exp(0) chain pads an odd count)
+    const int npair = cst.npair;
     double tA[HALF], tB[HALF];
     {
-        const double nim = cst.neg_inv_mu_l2e[0];
+        const double nim = npair ? cst.pair_nim[0] : cst.neg_inv_mu_l2e[0];
 #pragma unroll
         for (int j = 0; j < HALF; ++j) tA[j] = exp_scaled<CLAMPK>(tau[j], nim, tab_lane);
     }
+    // Pair units: tA holds x = t(R) of a virtual node R shared by two chain heads a > b (pa * a = pb * b = R):
+    // t(a) = x^pa into tA, t(b) = x^pb into tB by 3-4 multiplications, then the two chains; the second one evaluates
+    // the next unit's root into tA again.
+#pragma unroll 1
+    for (int p = 0; p < npair; ++p) {
+        const int type = cst.pair_type[p];
+#pragma unroll
+        for (int j = 0; j < HALF; ++j) {
+            tB[j] = tA[j] * tA[j];  // x^2
+            tA[j] = tA[j] * tB[j];  // x^3
+        }
+        if (type == 1) {
+#pragma unroll
+            for (int j = 0; j < HALF; ++j) tA[j] = tA[j] * tB[j];  // x^5
+        } else if (type == 2) {
+#pragma unroll
+            for (int j = 0; j < HALF; ++j) tB[j] = tB[j] * tB[j];  // x^4
+        }
+#pragma unroll
+        for (int j = 0; j < HALF; ++j) tB[j] = tB[j] * tA[j];  // x^5 (type 0), x^7 (types 1, 2)
+        const int lenA = cst.pair_lenA[p];
+#pragma unroll 1
+        for (int k = 1; k < lenA; ++k) {
+            sweep(tA, cst.cmu[slot++]);
+#pragma unroll
+            for (int j = 0; j < HALF; ++j) tA[j] = tA[j] * tA[j] * tA[j];
+        }
+        sweep(tA, cst.cmu[slot++]);
+        chain(tB, tA, cst.pair_lenB[p], cst.pair_nim[p + 1]);
+    }
     for (int ic = 0; ic < nchain; ic += 2) {
-        chain(tA, tB, ic);
-        chain(tB, tA, ic + 1);
+        chain(tA, tB, cst.chain_len[ic], cst.neg_inv_mu_l2e[ic + 1]);
+        chain(tB, tA, cst.chain_len[ic + 1], cst.neg_inv_mu_l2e[ic + 2]);
     }
 }
 

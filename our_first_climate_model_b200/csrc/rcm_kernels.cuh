@@ -10,6 +10,7 @@ constexpr int NLAY = RCM_NLAYER;
 constexpr int NLEV = RCM_NLEVEL;
 constexpr int MAX_ANGLE = 64;
 constexpr int MAX_TPERT = 16;
+constexpr int MAX_PAIR = 16;       // pair units of the angle schedule (DevConst)
 constexpr int HALF = NLAY / 2;     // layers owned by each lane of a pair
 constexpr int RCM_LBL_C = 16, RCM_LBL_NT = 128;  // tile shape of the LBL radiative-transfer kernel
 // The solver's exp (exp_scaled): table 2^(j/EXP_TAB) in shared memory, EXP_REP copies of every entry side by side
@@ -48,6 +49,14 @@ struct DevConst {
     double neg_inv_mu_l2e[MAX_ANGLE + 2];  // per CHAIN: -1/mu of its head, times 64/ln2 (argument scaling of exp_scaled)
     double cmu[MAX_ANGLE + 2];             // per SLOT: 2*pi*mu*dmu (0 for a padding slot)
     double csum;                           // sum of cmu over all nodes
+    // Pair units (visited before the chains; their slots come first in cmu).  Two chain heads a > b whose node numbers
+    // n = 2i+1 satisfy pa * a = pb * b = R with (pa, pb) = (3,5), (5,7) or (3,7) share ONE exp: x = t(R) at a virtual
+    // node, t(a) = x^pa, t(b) = x^pb by 3-4 multiplications.  Every unit's root is evaluated during the last sweep of
+    // the unit before it; pair_nim[p] is the root of unit p, pair_nim[npair] = 0.
+    int npair;
+    int pair_type[MAX_PAIR];               // 0: x^3, x^5   1: x^5, x^7   2: x^3, x^7
+    int pair_lenA[MAX_PAIR], pair_lenB[MAX_PAIR];  // slots of the cube chains below the two heads
+    double pair_nim[MAX_PAIR + 1];         // -1/mu of the virtual root, times EXP_TAB/ln2
     double expc[4];                        // Horner coefficients of exp_scaled, lowest order first
     // LBL band edges etc. live in global memory
 };

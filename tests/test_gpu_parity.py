@@ -75,6 +75,24 @@ def test_radiative_transfer_given_tau(solver, rcm, golden, n, cubes):
     assert relerr(dE, golden[f"s1_dE_{n}"]) < 1e-9  # and relative to max|dE| of the column
 
 
+@pytest.mark.parametrize("n", [20, 100])
+def test_angle_pair_units_on_and_off(solver, rcm, golden, n):
+    """RCM_OPT_ANGLE_PAIRS: chain heads that share a virtual root take it from one exp (default) - against the golden
+    fluxes with and without, and against each other (same mu values, other summation order and a few more roundings)."""
+    out = {}
+    for pairs in (1, 0):
+        solver.set_option(4, pairs)
+        load(solver, rcm, golden, n)
+        solver.advance(1)
+        st = solver.get_state()
+        assert relerr(st["E_down"], golden[f"s1_E_down_{n}"]) < RTOL
+        assert relerr(st["E_up"], golden[f"s1_E_up_{n}"]) < RTOL
+        out[pairs] = st
+    solver.set_option(4, 1)
+    assert relerr(out[1]["E_up"], out[0]["E_up"]) < 1e-13 and relerr(out[1]["E_down"], out[0]["E_down"]) < 1e-13
+    assert not np.array_equal(out[1]["E_up"], out[0]["E_up"])  # the option really changes the schedule
+
+
 @pytest.mark.parametrize("n", [10, 20, 100])
 def test_one_fused_step(solver, rcm, golden, n):
     load(solver, rcm, golden, n)
