@@ -433,26 +433,40 @@ __global__ void __launch_bounds__(NT, min_ctas(NT)) rcm_step_kernel(const StepAr
                     prep_tau_indices(s, tid);
                     __syncthreads();
                 }
-                if (tid < C) {  // theta-sort, one thread per column (main.cpp:536-540)
-                    double th[NLAY];
+                // theta-sort (main.cpp:536-540) by ranking, all threads: element (layer l, column c) goes to layer
+                // rank = #{l' : theta[l'] > theta[l], or equal and l' < l} (descending; any correct sort gives the
+                // reference's values).  One thread per column running a sorting network took 4 % of all warp-time - the
+                // other three warps of the CTA waiting at the barrier behind it.  s.invT (rebuilt below) holds theta,
+                // s.dE (rebuilt by K4) the change against the previous sorted profile.
+                for (int i = tid; i < NLAY * C; i += NT) {
+                    const int r = i / C;
+                    s.invT[i] = s.T[i] * cst.conv[r < HALF ? r : 29 - r];
+                }
+                __syncthreads();
+                for (int i = tid; i < NLAY * C; i += NT) {
+                    const int r = i / C, cc = i % C, l = r < HALF ? r : 29 - r;
+                    const double my = s.invT[i];
+                    int rank = 0;
 #pragma unroll
-                    for (int l = 0; l < NLAY; ++l) th[l] = s.T[prow(l) * C + tid] * cst.conv[l];
-#pragma unroll
-                    for (int pass = 0; pass < NLAY; ++pass) {
-#pragma unroll
-                        for (int l = (pass & 1); l + 1 < NLAY; l += 2) cex(th[l], th[l + 1]);
+                    for (int l2 = 0; l2 < NLAY; ++l2) {
+                        const double v = s.invT[prow(l2) * C + cc];
+                        rank += (v > my || (v == my && l2 < l)) ? 1 : 0;
                     }
+                    const double Tn = my / cst.conv[rank];
+                    s.T[prow(rank) * C + cc] = Tn;
+                    double d = 0.0;
+                    if (cc < ncl) {
+                        const size_t gi = (size_t)(col0 + cc) * NLAY + rank;
+                        d = fabs(Tn - a.Tprev[gi]);
+                        a.Tprev[gi] = Tn;
+                    }
+                    s.dE[rank * C + cc] = d;
+                }
+                __syncthreads();
+                if (tid < C) {
                     double dmax = 0.0;
 #pragma unroll
-                    for (int l = 0; l < NLAY; ++l) {
-                        const double Tn = th[l] / cst.conv[l];
-                        s.T[prow(l) * C + tid] = Tn;
-                        if (tid < ncl) {
-                            const size_t gi = (size_t)(col0 + tid) * NLAY + l;
-                            dmax = fmax(dmax, fabs(Tn - a.Tprev[gi]));
-                            a.Tprev[gi] = Tn;
-                        }
-                    }
+                    for (int l = 0; l < NLAY; ++l) dmax = fmax(dmax, s.dE[l * C + tid]);
                     s.dt[tid] = dmax;  // parked here until the diagnostics are written
                 }
                 __syncthreads();
