@@ -617,34 +617,39 @@ __global__ void __launch_bounds__(NT, min_ctas(NT)) rcm_step_kernel(const StepAr
             __syncthreads();
 
             const bool last = (step == a.nsteps - 1);
-            if (MODE == MODE_STEP && tid < C) {
+            if (MODE == MODE_STEP) {
                 // ------------- K5b: time step and temperature update (main.cpp:156-176) ---------
-                double mx = s.dE[tid], mabs = 0.0;
+                // the column's time step by one thread per column, the update of its 20 layers by all threads
+                if (tid < C) {
+                    double mx = s.dE[tid], mabs = 0.0;
 #pragma unroll
-                for (int l = 0; l < NLAY; ++l) {
-                    const double d = s.dE[l * C + tid];
-                    if (mx < d) mx = d;
-                    mabs = fmax(mabs, fabs(d));
-                }
-                double dt = (double)(float)cst.max_dT / mx * (1004.0 * cst.dp * 100.0) / 9.80665;
-                if (dt > cst.dt_cap) dt = cst.dt_cap;
-                const double dT_stat = s.dt[tid];
-#pragma unroll
-                for (int l = 0; l < NLAY; ++l)
-                    s.T[prow(l) * C + tid] += s.dE[l * C + tid] * dt * 9.80665 / (1004.0 * cst.dp * 100.0);
-                const double Tsn = s.T[prow(NLAY - 1) * C + tid] * cst.conv[NLAY - 1];
-                s.Ts[tid] = Tsn;
-                s.dt[tid] = dt;
-                if (tid < ncl) {
-                    const int col = col0 + tid;
-                    a.time_h[col] += (float)dt / 3600;  // main.cpp:581
-                    if (a.diag) {
-                        double* dg = a.diag + ((size_t)step * a.diag_ncol + col) * 4;
-                        dg[0] = s.solar[tid] - s.Eu[tid];
-                        dg[1] = dT_stat;
-                        dg[2] = mabs;
-                        dg[3] = dt;
+                    for (int l = 0; l < NLAY; ++l) {
+                        const double d = s.dE[l * C + tid];
+                        if (mx < d) mx = d;
+                        mabs = fmax(mabs, fabs(d));
                     }
+                    double dt = (double)(float)cst.max_dT / mx * (1004.0 * cst.dp * 100.0) / 9.80665;
+                    if (dt > cst.dt_cap) dt = cst.dt_cap;
+                    const double dT_stat = s.dt[tid];
+                    s.dt[tid] = dt;
+                    if (tid < ncl) {
+                        const int col = col0 + tid;
+                        a.time_h[col] += (float)dt / 3600;  // main.cpp:581
+                        if (a.diag) {
+                            double* dg = a.diag + ((size_t)step * a.diag_ncol + col) * 4;
+                            dg[0] = s.solar[tid] - s.Eu[tid];
+                            dg[1] = dT_stat;
+                            dg[2] = mabs;
+                            dg[3] = dt;
+                        }
+                    }
+                }
+                __syncthreads();
+                for (int i = tid; i < NLAY * C; i += NT) {
+                    const int l = i / C, cc = i % C;
+                    const double Tn = s.T[prow(l) * C + cc] + s.dE[i] * s.dt[cc] * 9.80665 / (1004.0 * cst.dp * 100.0);
+                    s.T[prow(l) * C + cc] = Tn;
+                    if (l == NLAY - 1) s.Ts[cc] = Tn * cst.conv[NLAY - 1];  // main.cpp:173
                 }
             }
             __syncthreads();
