@@ -206,14 +206,26 @@ __device__ __forceinline__ void sweep_item(const double (&tau)[HALF], const doub
 #pragma unroll
         for (int j = 0; j < HALF; ++j) tB[j] = tB[j] * tA[j];  // x^5 (type 0), x^7 (types 1, 2)
         const int lenA = cst.pair_lenA[p];
+        int lenB = cst.pair_lenB[p];
 #pragma unroll 1
         for (int k = 1; k < lenA; ++k) {
             sweep(tA, cst.cmu[slot++]);
 #pragma unroll
             for (int j = 0; j < HALF; ++j) tA[j] = tA[j] * tA[j] * tA[j];
         }
-        sweep(tA, cst.cmu[slot++]);
-        chain(tB, tA, cst.pair_lenB[p], cst.pair_nim[p + 1]);
+        if (lenB > 1) {
+            // the last angle of the first chain and the first one of the second in ONE block: four independent
+            // recurrences (a sweep on its own is latency-bound: 2.2x the time per instruction of the other blocks)
+            sweep(tA, cst.cmu[slot]);
+            sweep(tB, cst.cmu[slot + 1]);
+            slot += 2;
+#pragma unroll
+            for (int j = 0; j < HALF; ++j) tB[j] = tB[j] * tB[j] * tB[j];
+            --lenB;
+        } else {
+            sweep(tA, cst.cmu[slot++]);
+        }
+        chain(tB, tA, lenB, cst.pair_nim[p + 1]);
     }
     for (int ic = 0; ic < nchain; ic += 2) {
         chain(tA, tB, cst.chain_len[ic], cst.neg_inv_mu_l2e[ic + 1]);
@@ -249,7 +261,8 @@ struct Smem {
     static constexpr size_t PART = 2 * (size_t)NLEV * C;  // doubles of one wavelength group's partial fluxes [42][C]
     static constexpr size_t EP_BYTES = STAGE ? (size_t)NW * ROWBUF : (size_t)G * PART * sizeof(double);
     static_assert(!STAGE || (G == NW && NW >= 3 && (PART + NLEV * C) * sizeof(double) <= (size_t)ROWBUF), "one warp per wavelength group");
-    double* exp_tab;  // [64][16]
+    double* exp_tab;  // [EXP_TAB][EXP_REP]
+    double* plk;      // [2][PLK_MAX] Planck factors per wavelength (tables of up to PLK_MAX wavelengths)
     double* T;        // [20][C] layer temperature (sorted), rows in pair order
     double* invT;     // [20][C]
     double* delT;     // [20][C]
@@ -270,7 +283,7 @@ struct Smem {
     int* outside;     // [20] then [10]: some column of the tile needs a row beyond the two candidates
     static constexpr size_t ep_stride = STAGE ? (size_t)ROWBUF : PART * sizeof(double);
     static size_t bytes(int nactive) {
-        return ((size_t)EXP_TAB * EXP_REP + 3 * (size_t)NLAY * C + (size_t)nactive * NLAY * C + 5 * (size_t)C +
+        return ((size_t)EXP_TAB * EXP_REP + 2 * PLK_MAX + 3 * (size_t)NLAY * C + (size_t)nactive * NLAY * C + 5 * (size_t)C +
                 (STAGE ? 0 : 2 * (size_t)NLEV * C + (size_t)NLAY * C)) * sizeof(double) + EP_BYTES +
                (2 * (size_t)NLAY * C + (NCAND + 3) * NLAY + HALF + 2) * sizeof(int);
     }
@@ -282,6 +295,7 @@ struct Smem {
         invT = p;    p += NLAY * C;
         delT = p;    p += NLAY * C;
         vmr = p;     p += nactive * NLAY * C;
+        plk = p;     p += 2 * PLK_MAX;
         Ts = p;      p += C;
         invTs = p;   p += C;
         dt = p;      p += C;
@@ -335,6 +349,14 @@ __global__ void __launch_bounds__(NT, min_ctas(NT)) rcm_step_kernel(const StepAr
     for (int i = tid; i < EXP_TAB * EXP_REP; i += NT) s.exp_tab[i] = a.exp_tab[i / EXP_REP];
     const unsigned tab_lane = (unsigned)__cvta_generic_to_shared(s.exp_tab + (lane & (EXP_REP - 1)));
     const int nwvl = cst.nwvl;
+    // Planck factors of a repwvl-sized table live in shared memory (the per-wavelength global loads sat on the long
+    // scoreboard in front of K2); bigger spectral grids (rcm_set_spectral_grid) read them from global memory
+    const bool plk_smem = nwvl <= PLK_MAX;
+    if (plk_smem)
+        for (int i = tid; i < nwvl; i += NT) {
+            s.plk[i] = a.planck_c[i];
+            s.plk[PLK_MAX + i] = a.planck_k[i];
+        }
     // row staging (STAGE): this warp's buffer
     const bool stage = SM::STAGE && MODE == MODE_STEP && a.stage_rows;
     const int warp = tid >> 5;
@@ -574,7 +596,8 @@ __global__ void __launch_bounds__(NT, min_ctas(NT)) rcm_step_kernel(const StepAr
                 if (stage && item + 1 < nitem) request_rows(min(w_any + G, nwvl - 1));
                 // K2: Planck source B = k_w / (exp(c_w / T) - 1) (main.cpp:188-191 regrouped so that everything
                 // that depends on the wavelength alone is precomputed on the host); surface: main.cpp:301
-                const double pc = __ldg(a.planck_c + w), pk = real ? __ldg(a.planck_k + w) : 0.0;
+                const double pc = plk_smem ? s.plk[w] : __ldg(a.planck_c + w);
+                const double pk = !real ? 0.0 : plk_smem ? s.plk[PLK_MAX + w] : __ldg(a.planck_k + w);
 #pragma unroll
                 for (int j = 0; j < HALF; ++j)
                     Bo[j] = div_fast(pk, exp_scaled<false>(pc, s.invT[sb + j * C] * L2E64, tab_lane) - 1.0);

@@ -10,6 +10,7 @@ constexpr int NLAY = RCM_NLAYER;
 constexpr int NLEV = RCM_NLEVEL;
 constexpr int MAX_ANGLE = 64;
 constexpr int MAX_TPERT = 16;
+constexpr int PLK_MAX = 128;       // wavelengths whose Planck factors the step kernel keeps in shared memory
 constexpr int MAX_PAIR = 16;       // pair units of the angle schedule (DevConst)
 constexpr int HALF = NLAY / 2;     // layers owned by each lane of a pair
 constexpr int RCM_LBL_C = 16, RCM_LBL_NT = 128;  // tile shape of the LBL radiative-transfer kernel
