@@ -35,10 +35,10 @@ UNIT = "updates/s"
 # expression tree: 31 exp, 33 divides, ~520 add/mul/fma.
 ALG_EXP, ALG_DIV, ALG_FMA = 31, 33, 520
 # FP64-pipe instructions this repo's kernel really executes per unit, and DRAM bytes per column-step:
-# from the ncu capture committed under profiles/ (r1c_ncu_step_kernel_regions.md: 1,546,371,072 FP64 warp
-# instructions and 85.5 + 24.1 MB of DRAM traffic for one launch of 65,536 columns x 100 wavelengths x 20 layers).
-EXEC_FP64_PER_UNIT = 377.5
-DRAM_BYTES_PER_COLUMN_STEP = 1671.0
+# from the ncu capture committed under profiles/ (r1f_ncu_step_kernel_regions.md: 1,377,349,632 FP64 warp
+# instructions and 85.9 + 24.7 MB of DRAM traffic for one launch of 65,536 columns x 100 wavelengths x 20 layers).
+EXEC_FP64_PER_UNIT = 336.3
+DRAM_BYTES_PER_COLUMN_STEP = 1688.0
 
 
 def _env_int(name, default):
