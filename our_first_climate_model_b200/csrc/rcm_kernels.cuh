@@ -37,7 +37,7 @@ struct DevConst {
     // (repwvl_thermal.cpp:202, :214, :226, :240).  ip/player/conv are indexed by the top-down layer l;
     // ipcell/delP/numDens/tref_ip by the pair-order row (l for l<10, 29-l otherwise).
     int ip[NLAY];
-    int ipcell[NLAY];  // ip * (n_tpert-1): first table cell of the layer's pressure interval
+    int ipcell[NLAY];  // row * (n_tpert-1): first cell of the layer's block in the per-layer coefficient table
     int cloud_row;     // pair-order row of the cloud layer, -1 if none
     double delP[NLAY], numDens[NLAY], tref_ip[NLAY], player[NLAY], conv[NLAY];
     double t_pert[MAX_TPERT];
@@ -47,7 +47,7 @@ struct DevConst {
     // [nchain] of neg_inv_mu_l2e is 0 (the pipelined loop evaluates it and never uses the result).
     int nslot, nchain;
     int chain_len[MAX_ANGLE + 2];          // slots of chain i (>= 1)
-    double neg_inv_mu_l2e[MAX_ANGLE + 2];  // per CHAIN: -1/mu of its head, times 64/ln2 (argument scaling of exp_scaled)
+    double neg_inv_mu_l2e[MAX_ANGLE + 2];  // per CHAIN: -1/mu of its head, times EXP_TAB/ln2 (argument scaling of exp_scaled)
     double cmu[MAX_ANGLE + 2];             // per SLOT: 2*pi*mu*dmu (0 for a padding slot)
     double csum;                           // sum of cmu over all nodes
     // Pair units (visited before the chains; their slots come first in cmu).  Two chain heads a > b whose node numbers
@@ -68,7 +68,7 @@ struct StepArgs {
     int diag_ncol;       // columns of the whole ensemble = row length of diag
     int C;               // columns per tile
     int nthreads;        // threads per CTA (2 * C * wavelength groups)
-    int stage_rows;      // 1: the next wavelength's table rows travel into shared memory (cp.async.bulk) during the angle loop
+    int stage_rows;      // 1: the next wavelength's table rows travel into shared memory (cp.async) during the angle loop
     int clampk;          // 1: exp_scaled clamps its exponent itself (angle schedules where tau_clamp would bite)
     double tau_clamp;    // tau is clamped to this before the transmissions are evaluated (see exp_scaled)
     int ntiles;
@@ -94,7 +94,7 @@ struct StepArgs {
     // component paths
     double* tau_io;        // [ncol][nwvl][20]  (written by MODE_TAU, read by MODE_RT)
     int* lowpos_t;         // [ncol][20] bottom-up (MODE_TAU)
-    const double* exp_tab; // [64] 2^(j/64)
+    const double* exp_tab; // [EXP_TAB] 2^(j/EXP_TAB), high words prepared for exp_scaled (rcm_create)
     int h2o_slot;          // position of H2O in the active list, -1 if absent
     // per-column solar forcing / grey-cloud optical depth (rcm_set_column_solar); NULL = the ensemble-wide constants
     const double* solar_col;  // [ncol] absorbed solar irradiance, W/m2 (main.cpp:255-264 per column)
