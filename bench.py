@@ -143,6 +143,15 @@ def cpu_throughput(nwvl, cols_per_core, nsteps, repeats=1):
     return units / statistics.median(walls), cores, kind, walls
 
 
+def workload_config(ncol, nwvl, world):
+    """`config` of the JSON line - the same for this repo's arm and the reference arm."""
+    return {"workload": f"{ncol}-column synthetic perturbed-profile ensemble per GPU, repwvl-{nwvl} "
+                        "RCE step (BASELINE configs[3])", "columns_per_gpu": ncol, "nwvl": nwvl,
+            "nlayer": NLAY, "nangle": 30, "parallelism": f"columns sharded over {world} GPU(s)",
+            "l2": "no flush: per-step working set (state + fluxes, ~130 MB at 65,536 columns) exceeds the "
+                  "126 MB L2 and the kernel is FP64-pipe bound (DRAM < 1% of peak)"}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return 0
@@ -160,9 +169,9 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"synthetic perturbed-profile ensemble, repwvl-{args.nwvl}, one RCE step "
-                                   f"(main.cpp:531-583); CPU sample of {cols} columns per core", "nwvl": args.nwvl,
-                       "nlayer": NLAY, "nangle": 30},
+            "config": dict(workload_config(args.ncol, args.nwvl, args.gpus),
+                           sample=f"each bench step = {cols} columns x 1 reference iteration (main.cpp:531-583) per "
+                                  f"host core, a bounded sample of that workload"),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -288,11 +297,7 @@ def run_b200(args, rank, world, local_rank):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{ncol}-column synthetic perturbed-profile ensemble per GPU, repwvl-{nwvl} "
-                                   "RCE step (BASELINE configs[3])", "columns_per_gpu": ncol, "nwvl": nwvl,
-                       "nlayer": NLAY, "nangle": 30, "parallelism": f"columns sharded over {world} GPU(s)",
-                       "l2": "no flush: per-step working set (state + fluxes, ~130 MB at 65,536 columns) exceeds the "
-                             "126 MB L2 and the kernel is FP64-pipe bound (DRAM < 1% of peak)"},
+            "config": workload_config(ncol, nwvl, world),
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_s / args.steps, "api": "rcm_step_host (pinned host buffers; columns travel in 8 chunks through 3 streams, copies overlap the step)",
