@@ -314,6 +314,11 @@ int ensure_columns(rcm_solver* s, int ncol) {
     s->cap = ncol;
     s->diag_steps = 0;
     s->part_cap = 0;
+    // the per-column forcing buffers follow the capacity: reallocated by the next rcm_set_column_solar / checkpoint load
+    if (s->d_solar_col) cudaFree(s->d_solar_col);
+    if (s->d_cloud_col) cudaFree(s->d_cloud_col);
+    s->d_solar_col = s->d_cloud_col = nullptr;
+    s->has_col_solar = s->has_col_cloud = false;
     return RCM_OK;
 }
 
@@ -1045,8 +1050,13 @@ int rcm_load_checkpoint(rcm_solver* s, const char* path) {
     }
     s->ncol = (int)hdr[0];
     if ((hdr[4] || hdr[5]) && !s->d_solar_col) {
-        CU(dalloc(s->d_solar_col, (size_t)s->cap));
-        CU(dalloc(s->d_cloud_col, (size_t)s->cap));
+        cudaError_t e = dalloc(s->d_solar_col, (size_t)s->cap);
+        if (e == cudaSuccess) e = dalloc(s->d_cloud_col, (size_t)s->cap);
+        if (e != cudaSuccess) {
+            std::fclose(f);
+            s->ncol = 0;
+            return cuda_fail(s, e, "checkpoint: per-column forcing buffers");
+        }
     }
     CkptArray arr[12];
     const int na = ckpt_arrays(s, arr, hdr[4] != 0, hdr[5] != 0);

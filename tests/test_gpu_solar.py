@@ -147,3 +147,25 @@ def test_column_solar_argument_errors(rcm):
         s2.set_column_solar(sp)
     s.close()
     s2.close()
+
+
+def test_column_solar_after_the_ensemble_grew(rcm, port):
+    """Capacity regression: forcing buffers allocated for a small ensemble must follow a later, bigger rcm_set_columns."""
+    s = rcm.Solver(0)
+    s.set_repwvl_table_from(rcm.Table(table_path(10)))
+    pl, st, Ts = ensemble(rcm, 8, 3)
+    s.set_columns(pl, st["Tlayer"], Ts, st["vmr9"], st["rel_hum"])
+    s.set_column_solar(None, *forcing(8, 1))
+    n = 5000
+    pl, st, Ts = ensemble(rcm, n, 4)
+    s.set_columns(pl, st["Tlayer"], Ts, st["vmr9"], st["rel_hum"])
+    tau_s, mu_s, alb = forcing(n, 2)
+    f = s.set_column_solar(None, tau_s, mu_s, alb, cloud_from_tau_s=True)
+    s.advance(1)
+    got = s.get_state()
+    tab = port.load_rcmtab(table_path(10))
+    for c in (0, 4999):
+        ref = port.advance(tab, pl, st["rel_hum"][c], f["solar_irr"][c], st["Tlayer"][c], Ts[c], st["vmr9"][c], 1, tau_s=tau_s[c])
+        assert relerr(got["E_up"][c:c + 1], ref["E_up"]) < 1e-10
+        np.testing.assert_allclose(got["dE"][c], ref["dE"][0], rtol=0, atol=1e-9 * np.abs(ref["dE"]).max())
+    s.close()
