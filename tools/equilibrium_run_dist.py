@@ -1,8 +1,10 @@
-"""BASELINE configs[3] over N GPUs: ONE 65,536-column synthetic ensemble (repwvl-100) sharded across the ranks of a
-torchrun launch and stepped until every column is stationary (strong scaling: total work fixed).
+"""BASELINE configs[3] / configs[4] over N GPUs: ONE synthetic ensemble sharded across the ranks of a torchrun launch
+and stepped until every column is stationary (strong scaling: total work fixed).  Default: 65,536 columns, repwvl-100
+(configs[3]); with a fifth argument `lbl:NWVL`: a line-by-line ensemble with 2xCO2 on NWVL synthetic wavelengths
+(configs[4], e.g. 4096 columns).
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29555 \
-        tools/equilibrium_run_dist.py [ncol_total] [max_steps] [threshold_K_per_step] [check_every]
+        tools/equilibrium_run_dist.py [ncol_total] [max_steps] [threshold_K_per_step] [check_every] [lbl:NWVL]
 
 Every rank generates the same ensemble (seeded) and keeps its contiguous shard; between checks nothing crosses
 GPUs; each check is one allreduce of the block's four scalars (distributed.run_to_equilibrium).  Time is the maximum
@@ -19,6 +21,7 @@ ncol = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 max_steps = int(sys.argv[2]) if len(sys.argv) > 2 else 6000
 thr = float(sys.argv[3]) if len(sys.argv) > 3 else 1e-3
 check_every = int(sys.argv[4]) if len(sys.argv) > 4 else 250
+lbl_nwvl = int(sys.argv[5].split(":")[1]) if len(sys.argv) > 5 and sys.argv[5].startswith("lbl:") else 0
 
 world = int(os.environ.get("WORLD_SIZE", 1))
 local = int(os.environ.get("LOCAL_RANK", 0))
@@ -27,14 +30,22 @@ rank = 0
 if world > 1:
     rank, world = rdist.init("nccl")
 lo, hi = rdist.shard_range(ncol, rank, world)
-st = bench.build_ensemble(rcm, ncol, 12345)
+if lbl_nwvl:
+    case = bench.build_lbl_case(rcm, ncol, lbl_nwvl, 4242)
+    st = dict(case["st"], plevel=case["pl"], Tsurf=case["Tsurf"])
+else:
+    st = bench.build_ensemble(rcm, ncol, 12345)
 p = rcm.default_params()
 p.dT_converged = thr
 s = rcm.Solver(local, p)
 stream = torch.cuda.Stream()  # the solver launches on this torch stream: events and NCCL see its work
 torch.cuda.set_stream(stream)
 s.set_stream(stream.cuda_stream)
-s.set_repwvl_table_from(rcm.Table(os.path.join(bench.GOLDEN, "Reduced100Forcing.rcmtab")))
+if lbl_nwvl:
+    s.set_lbl_tables(case["wvl"], case["tau5"], case["h2o_ref"], case["o3_ref"], 2.0)
+else:
+    s.set_repwvl_table_from(rcm.Table(os.path.join(bench.GOLDEN, "Reduced100Forcing.rcmtab")))
+nwvl = s.nwvl
 s.set_columns(st["plevel"], st["Tlayer"][lo:hi].copy(), st["Tsurf"][lo:hi].copy(),
               np.ascontiguousarray(st["vmr9"][lo:hi]), st["rel_hum"][lo:hi].copy())
 s.advance(1)  # warm-up launch (module load, shared-memory attribute), then restart from the initial state
@@ -60,7 +71,8 @@ if rank == 0:
     steps = res["steps"]
     print(json.dumps({"tool": "equilibrium_run_dist", "n_gpus": world, "ncol_total": ncol, "steps": steps,
                       "check_every": check_every, "threshold_K_per_step": thr, "seconds": ms / 1e3,
-                      "ms_per_step": ms / steps, "updates_per_s": ncol * 100.0 * 20 * steps / (ms / 1e3),
+                      "ms_per_step": ms / steps, "workload": f"lbl 2xCO2, {nwvl} wavelengths" if lbl_nwvl else "repwvl-100", "nwvl": nwvl,
+                      "updates_per_s": ncol * float(nwvl) * 20 * steps / (ms / 1e3),
                       "converged_fraction": res["converged_fraction"], "max_dT": res["max_dT"],
                       "toa_net_mean_Wm2": res["toa_net_mean"], "Tsurf_mean": float(tsum[0]) / ncol,
                       "Tsurf_min": -float(tsum[1]), "Tsurf_max": float(tsum[2]),
