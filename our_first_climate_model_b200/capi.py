@@ -318,6 +318,13 @@ class Solver:
                                          C.c_int(npp)), self._h)
         self.nwvl = nw
 
+    def set_spectral_grid(self, wvl, weight):
+        """rcm_set_spectral_grid: wavelengths [nm] and spectral weights alone (for rcm_radiative_transfer with a tau
+        that was built elsewhere - the `radiative_transfer` signature of main.cpp:320-324)."""
+        w = _f64(wvl)
+        _check(_lib.rcm_set_spectral_grid(self._h, _p(w), _p(_f64(weight, (w.size,))), C.c_int(w.size)), self._h)
+        self.nwvl = w.size
+
     def set_repwvl_table_from(self, table: Table):
         _check(_lib.rcm_set_repwvl_table_from(self._h, table._h), self._h)
         self.nwvl = table.n_wvl

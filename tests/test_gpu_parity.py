@@ -75,6 +75,31 @@ def test_radiative_transfer_given_tau(solver, rcm, golden, n, cubes):
     assert relerr(dE, golden[f"s1_dE_{n}"]) < 1e-9  # and relative to max|dE| of the column
 
 
+@pytest.mark.parametrize("nw", [7, 150])
+def test_radiative_transfer_on_a_bare_spectral_grid(rcm, port, golden, nw):
+    """rcm_set_spectral_grid + rcm_radiative_transfer (what the `radiative_transfer` adapter does) with a tau that was built
+    elsewhere: 7 wavelengths, and 150 - more than the step kernel keeps Planck factors for in shared memory (PLK_MAX)."""
+    rng = np.random.default_rng(nw)
+    ncol = 13  # ragged: less than one 16-column tile
+    tab = port.load_rcmtab(table_path(100))
+    pick = rng.integers(0, 100, nw)
+    wvl = tab["wvl"][pick] * rng.uniform(0.98, 1.02, nw)
+    weight = tab["weight"][pick] * rng.uniform(0.5, 1.5, nw)
+    tau = golden["tau100"][:ncol][:, pick, :] * rng.uniform(0.5, 2.0, (ncol, nw, 1))
+    T = golden["Tlayer"][:ncol] + rng.uniform(-3, 3, (ncol, 20))
+    Ts = golden["Tsurf"][:ncol] + rng.uniform(-2, 2, ncol)
+    s = rcm.Solver(0)
+    s.set_spectral_grid(wvl, weight)
+    s.set_columns(golden["plevel"], T, Ts, golden["vmr9"][:ncol], golden["rel_hum"][:ncol])
+    Ed, Eu, dE = s.radiative_transfer(tau)
+    for c in range(ncol):
+        rEd, rEu, rdE = port.radiative_transfer(tau[c], wvl, weight, T[c], Ts[c], float(golden["solar_irr"]))
+        scale = np.abs(rEu).max()
+        assert np.max(np.abs(Ed[c] - rEd)) < RTOL * scale and np.max(np.abs(Eu[c] - rEu)) < RTOL * scale
+        assert np.max(np.abs(dE[c] - rdE)) < RTOL * scale
+    s.close()
+
+
 @pytest.mark.parametrize("n", [20, 100])
 def test_angle_pair_units_on_and_off(solver, rcm, golden, n):
     """RCM_OPT_ANGLE_PAIRS: chain heads that share a virtual root take it from one exp (default) - against the golden
