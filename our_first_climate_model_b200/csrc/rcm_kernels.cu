@@ -999,6 +999,7 @@ __global__ void __launch_bounds__(NT, 384 / NT) rcm_lbl_rt_kernel(const LblArgs 
     double* s_sO = p;  p += NLAY * C;
     double* s_Ts = p;  p += C;
     double* s_cl = p;  p += C;
+    double* s_B = p;   p += HALF * NT;  // [10][NT] Planck source of the thread's ten layers (written by a rolled loop)
     double* s_Ep = p;  // [21][GC]
     const int tid = threadIdx.x, lane = tid & 31;
     const int h = tid & 1, q = tid >> 1, c = q % C, g = q / C;
@@ -1047,7 +1048,14 @@ __global__ void __launch_bounds__(NT, 384 / NT) rcm_lbl_rt_kernel(const LblArgs 
             v = __dadd_rn(v, __ldg(t5 + 4 * plane + l));
             if (cst.cloud_row == h * HALF + j) v = __dadd_rn(v, s_cl[c]);
             tau[j] = CLAMPK ? v : fmin(v, a.tau_clamp);
-            const double B = cplkavg_narrow(lo, hi, whi, wlo, s_T[sb + j * C], tab_lane);
+        }
+        // The band-integrated Planck function of the ten layers in a ROLLED loop through shared memory: inlined ten
+        // times it made the kernel 9,900 instructions long and instruction fetch 6 % of its stalls.
+#pragma unroll 1
+        for (int j = 0; j < HALF; ++j) s_B[j * NT + tid] = cplkavg_narrow(lo, hi, whi, wlo, s_T[sb + j * C], tab_lane);
+#pragma unroll
+        for (int j = 0; j < HALF; ++j) {
+            const double B = s_B[j * NT + tid];
             Bo[j] = real ? B : 0.0;
         }
         const double Bsurf = cplkavg_narrow(lo, hi, whi, wlo, s_Ts[c], tab_lane);
@@ -1268,7 +1276,8 @@ cudaError_t rcm_launch_cplkavg(int n, const double* lo, const double* hi, const 
 }
 
 size_t rcm_lbl_smem_bytes(int C, int nthreads) {
-    return ((size_t)EXP_TAB * EXP_REP + (size_t)NLAY * C * 3 + 2 * C + (size_t)NLEV * (nthreads / 2)) * sizeof(double);
+    return ((size_t)EXP_TAB * EXP_REP + (size_t)NLAY * C * 3 + 2 * C + (size_t)HALF * nthreads +
+            (size_t)NLEV * (nthreads / 2)) * sizeof(double);
 }
 
 cudaError_t rcm_launch_lbl_step(const LblArgs& a, cudaStream_t st) {
