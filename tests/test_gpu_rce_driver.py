@@ -1,0 +1,78 @@
+"""The C++ ensemble RCE driver (csrc/host/rce_driver.cpp -> lib/rcm_rce): host code in the reference's language over the
+C ABI.  Its output rows (the reference's output_conv format) must equal what the same run gives through the Python
+binding; a run split by checkpoint / resume must give the same file."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, table_path
+
+pytestmark = pytest.mark.gpu
+
+
+def exe(rcm):
+    p = os.path.join(os.path.dirname(rcm.library_path()), "rcm_rce")
+    if not os.path.exists(p):
+        rcm.build_library()
+    return p
+
+
+def run(rcm, *args):
+    r = subprocess.run([exe(rcm), "--atm", os.path.join(GOLDEN, "column21.atm"), *args], capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0, r.stderr
+    return r.stdout
+
+
+def test_driver_rows_equal_the_python_path_and_resume(rcm, tmp_path):
+    ncol, seed, tab = 5, 12345, table_path(20)
+    out = str(tmp_path / "output.txt")
+    msg = run(rcm, "--table", tab, "--ncol", str(ncol), "--seed", str(seed), "--max-steps", "3", "--steps-exact", "--out", out)
+    assert "5 columns, 3 iterations" in msg
+    # the same run through the binding
+    atm = rcm.read_atm(os.path.join(GOLDEN, "column21.atm"))
+    pl = atm[:, 1].copy()
+    Tlev, vlev = rcm.make_ensemble(ncol, seed, pl, atm[:, 2].copy(), atm[:, 4:9].T.copy())
+    st = rcm.init_columns(pl, Tlev, vlev)
+    p = rcm.default_params()
+    p.dT_converged = 1e-3
+    s = rcm.Solver(0, p)
+    s.set_repwvl_table_from(rcm.Table(tab))
+    s.set_columns(pl, st["Tlayer"], 288.2, st["vmr9"], st["rel_hum"])
+    s.advance(3)
+    got = s.get_state()
+    s.close()
+    ref = str(tmp_path / "ref.txt")
+    rcm.write_profiles(ref, pl, got["Tlayer"], got["time_h"], header=True, column_ids=True)
+    assert open(out).read() == open(ref).read()
+    # two iterations, checkpoint, one more after a resume: the same file
+    ck, out2 = str(tmp_path / "run.ckpt"), str(tmp_path / "output2.txt")
+    run(rcm, "--table", tab, "--ncol", str(ncol), "--seed", str(seed), "--max-steps", "2", "--steps-exact", "--out", out2,
+        "--checkpoint", ck)
+    assert open(out2).read() != open(out).read()
+    run(rcm, "--table", tab, "--resume", ck, "--max-steps", "1", "--steps-exact", "--out", out2)
+    assert open(out2).read() == open(out).read()
+
+
+def test_driver_reaches_the_reference_equilibrium(rcm, golden, tmp_path):
+    """One column (the .atm file itself), Reduced100, 6,000 iterations: the surface temperature of the UNMODIFIED reference
+    after the same 6,000 iterations (golden vector, member 0 = the file's column) within the 1e-3 K of north_star; rows in
+    the reference's exact format (no column ids).  Then the stationarity stop."""
+    out = str(tmp_path / "output.txt")
+    msg = run(rcm, "--table", table_path(100), "--ncol", "1", "--max-steps", "6000", "--steps-exact", "--out", out)
+    ts = float(msg.split("member 0: T_surface ")[1].split(" K")[0])
+    assert abs(ts - float(golden["s6000_Tsurf_100"][0])) < 1e-3, msg
+    lines = open(out).read().splitlines()
+    assert lines[0] == "layer,player,Tlayer,theta,time" and len(lines) == 21 and lines[1].startswith("0,25.000000,")
+    msg = run(rcm, "--table", table_path(100), "--ncol", "3", "--max-steps", "6000", "--check-every", "500", "--dT", "1e-3",
+              "--out", out)
+    assert "3/3 stationary" in msg and int(msg.split(" columns, ")[1].split(" iterations")[0]) < 6000
+
+
+def test_driver_argument_errors(rcm, tmp_path):
+    r = subprocess.run([exe(rcm), "--atm", "/no/such.atm", "--table", table_path(10)], capture_output=True, text=True)
+    assert r.returncode == 1 and "rcm_rce:" in r.stderr
+    r = subprocess.run([exe(rcm), "--bogus"], capture_output=True, text=True)
+    assert r.returncode == 1
