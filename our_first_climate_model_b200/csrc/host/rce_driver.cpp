@@ -8,6 +8,11 @@
 //
 //   rcm_rce --atm test.atm --table Reduced100Forcing.nc [--ncol N] [--seed S] [--max-steps M] [--check-every K]
 //           [--dT 1e-3] [--device D] [--out output.txt] [--checkpoint file] [--resume file] [--steps-exact]
+//   rcm_rce --atm fpda.lbl.atm --lbl DIR [--co2-factor F] ...     line-by-line: DIR/lbl.{h2o,co2,o3,ch4,n2o}.asc
+//
+// The line-by-line form reads the five tables with the drop-in of ASCII_file2xy2D (lbl.arts/testlblarts.cpp:24-26 is the
+// reference's only call of that reader); a six-column .atm (lbl.arts/README:1-3) gets the well-mixed CO2 / CH4 / N2O of
+// lbl.arts/README:13-16.  The tables hold the optical depths of the file's own column: member 0's H2O and O3.
 //
 // --steps-exact runs exactly max_steps iterations (the reference's n_steps semantics, main.cpp:83) instead of
 // stopping at stationarity.  Exit code 0, or 1 with the library's error text on stderr.  No CPU fallback.
@@ -29,7 +34,8 @@ int die(const char* what, int st, const rcm_solver* s) {
 }  // namespace
 
 int main(int argc, char** argv) {
-    std::string atm_path, table_path, out_path = "output.txt", ckpt_path, resume_path;
+    std::string atm_path, table_path, lbl_dir, out_path = "output.txt", ckpt_path, resume_path;
+    double co2_factor = 1.0;
     int ncol = 1, device = 0, check_every = 250, steps_exact = 0;
     long max_steps = 6000;
     unsigned long long seed = 12345;
@@ -39,6 +45,8 @@ int main(int argc, char** argv) {
         auto val = [&]() -> const char* { return (i + 1 < argc) ? argv[++i] : ""; };
         if (a == "--atm") atm_path = val();
         else if (a == "--table") table_path = val();
+        else if (a == "--lbl") lbl_dir = val();
+        else if (a == "--co2-factor") co2_factor = std::atof(val());
         else if (a == "--ncol") ncol = std::atoi(val());
         else if (a == "--seed") seed = std::strtoull(val(), nullptr, 10);
         else if (a == "--max-steps") max_steps = std::atol(val());
@@ -54,8 +62,8 @@ int main(int argc, char** argv) {
             return 1;
         }
     }
-    if (atm_path.empty() || table_path.empty() || ncol < 1 || max_steps < 1 || check_every < 1) {
-        std::fprintf(stderr, "usage: rcm_rce --atm FILE --table FILE [--ncol N] [--seed S] [--max-steps M] [--check-every K] "
+    if (atm_path.empty() || (table_path.empty() == lbl_dir.empty()) || ncol < 1 || max_steps < 1 || check_every < 1) {
+        std::fprintf(stderr, "usage: rcm_rce --atm FILE (--table FILE | --lbl DIR [--co2-factor F]) [--ncol N] [--seed S] [--max-steps M] [--check-every K] "
                              "[--dT K/step] [--device D] [--out FILE] [--checkpoint FILE] [--resume FILE] [--steps-exact]\n");
         return 1;
     }
@@ -66,10 +74,16 @@ int main(int argc, char** argv) {
     int nrows = 0, nc = 0;
     int st = rcm_read_atm(atm_path.c_str(), NLEV, cols.data(), &nrows, &nc);
     if (st != RCM_OK) return die(atm_path.c_str(), st, nullptr);
-    if (nrows != NLEV || nc < 9) {
-        std::fprintf(stderr, "rcm_rce: %s: need 21 levels x 9 columns (z p T air H2O O3 CO2 CH4 N2O), got %d x %d\n",
-                     atm_path.c_str(), nrows, nc);
+    const bool lbl = !lbl_dir.empty();
+    if (nrows != NLEV || nc < (lbl ? 6 : 9)) {
+        std::fprintf(stderr, "rcm_rce: %s: need 21 levels x %d columns (z p T air H2O O3%s), got %d x %d\n", atm_path.c_str(),
+                     lbl ? 6 : 9, lbl ? "" : " CO2 CH4 N2O", nrows, nc);
         return 1;
+    }
+    if (nc < 9) {  // lbl.arts/README:13-16
+        const double well_mixed[3] = {400.0, 1.7, 0.315};
+        for (int k = 0; k < 3; ++k)
+            for (int i = 0; i < NLEV; ++i) cols[(6 + k) * NLEV + i] = well_mixed[k];
     }
     const double* plevel = &cols[1 * NLEV];
     const double* Tbase = &cols[2 * NLEV];
@@ -96,12 +110,44 @@ int main(int argc, char** argv) {
     rcm_solver* s = nullptr;
     st = rcm_create(device, &p, &s);
     if (st != RCM_OK) return die("rcm_create", st, nullptr);
-    rcm_table* t = nullptr;
-    st = rcm_table_load(table_path.c_str(), &t);
-    if (st != RCM_OK) return die(table_path.c_str(), st, s);
-    st = rcm_set_repwvl_table_from(s, t);
-    rcm_table_free(t);
-    if (st != RCM_OK) return die("rcm_set_repwvl_table_from", st, s);
+    if (lbl) {
+        // the five species tables, README order of the composition: H2O, CO2, O3, CH4, N2O (rcm_set_lbl_tables)
+        const char* names[5] = {"h2o", "co2", "o3", "ch4", "n2o"};
+        std::vector<double> wvl, tau5;
+        int nwvl = 0;
+        for (int k = 0; k < 5; ++k) {
+            const std::string path = lbl_dir + "/lbl." + names[k] + ".asc";
+            int nx = 0, ny = 0;
+            double *x = nullptr, *y = nullptr;
+            const int rc = rcm_ascii_file2xy2D(path.c_str(), &nx, &ny, &x, &y);  // 0, or the reference's -1 / -2 / -5
+            if (rc != 0 || ny != NLAY || nx < 2 || (k > 0 && nx != nwvl)) {
+                std::fprintf(stderr, "rcm_rce: %s: reader status %d, %d wavelengths x %d layers (need the same wavelengths in "
+                                     "all five files and 20 layers)\n", path.c_str(), rc, nx, ny);
+                return 1;
+            }
+            if (k == 0) {
+                nwvl = nx;
+                wvl.assign(x, x + nx);
+                tau5.resize((size_t)5 * nx * NLAY);
+            } else if (std::memcmp(wvl.data(), x, (size_t)nx * sizeof(double)) != 0) {
+                std::fprintf(stderr, "rcm_rce: %s: wavelength grid differs from lbl.h2o.asc\n", path.c_str());
+                return 1;
+            }
+            std::memcpy(&tau5[(size_t)k * nx * NLAY], y, (size_t)nx * NLAY * sizeof(double));
+            rcm_free(x);
+            rcm_free(y);
+        }
+        // reference profiles of the tables = the .atm file's own column = member 0 (layer VMRs, species 0 and 2 of vmr9)
+        st = rcm_set_lbl_tables(s, wvl.data(), tau5.data(), nwvl, &vmr9[0 * NLAY], &vmr9[2 * NLAY], co2_factor);
+        if (st != RCM_OK) return die("rcm_set_lbl_tables", st, s);
+    } else {
+        rcm_table* t = nullptr;
+        st = rcm_table_load(table_path.c_str(), &t);
+        if (st != RCM_OK) return die(table_path.c_str(), st, s);
+        st = rcm_set_repwvl_table_from(s, t);
+        rcm_table_free(t);
+        if (st != RCM_OK) return die("rcm_set_repwvl_table_from", st, s);
+    }
     if (!resume_path.empty()) {
         st = rcm_load_checkpoint(s, resume_path.c_str());
         if (st != RCM_OK) return die(resume_path.c_str(), st, s);

@@ -71,6 +71,42 @@ def test_driver_reaches_the_reference_equilibrium(rcm, golden, tmp_path):
     assert "3/3 stationary" in msg and int(msg.split(" columns, ")[1].split(" iterations")[0]) < 6000
 
 
+def test_driver_line_by_line_mode(rcm, tmp_path):
+    """--lbl DIR: the five species tables written in the reference's text format (lbl.arts/README:5-11), read back by the
+    drop-in of ASCII_file2xy2D inside the C++ driver, two iterations with 2xCO2 - same rows as the Python path."""
+    lbl_atm = os.path.join(GOLDEN, "column21.lbl.atm")      # six columns: z p T air H2O O3 (lbl.arts/README:1-3)
+    atm = rcm.read_atm(lbl_atm)
+    assert atm.shape[1] == 6
+    pl = atm[:, 1].copy()
+    vbase = np.stack([atm[:, 4], atm[:, 5], np.full(21, 400.0), np.full(21, 1.7), np.full(21, 0.315)])  # README:13-16
+    ncol, seed, nwvl = 6, 77, 700
+    Tlev, vlev = rcm.make_ensemble(ncol, seed, pl, atm[:, 2].copy(), vbase)
+    st = rcm.init_columns(pl, Tlev, vlev)
+    h2o_ref, o3_ref = st["vmr9"][0, 0].copy(), st["vmr9"][0, 2].copy()
+    wvl, tau5 = rcm.make_lbl_tables(nwvl, 777, pl, h2o_ref, o3_ref)
+    d = tmp_path / "lbl"
+    d.mkdir()
+    for k, nm in enumerate(["h2o", "co2", "o3", "ch4", "n2o"]):
+        rcm.write_lbl_asc(str(d / f"lbl.{nm}.asc"), wvl, tau5[k])
+    out = str(tmp_path / "output.txt")
+    r = subprocess.run([exe(rcm), "--atm", lbl_atm, "--lbl", str(d), "--co2-factor", "2", "--ncol", str(ncol), "--seed", str(seed),
+                        "--max-steps", "2", "--steps-exact", "--out", out], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    s = rcm.Solver(0)
+    s.set_lbl_tables(wvl, tau5, h2o_ref, o3_ref, 2.0)
+    s.set_columns(pl, st["Tlayer"], 288.2, st["vmr9"], st["rel_hum"])
+    s.advance(2)
+    got = s.get_state()
+    s.close()
+    ref = str(tmp_path / "ref.txt")
+    rcm.write_profiles(ref, pl, got["Tlayer"], got["time_h"], header=True, column_ids=True)
+    assert open(out).read() == open(ref).read()
+    # a table with another wavelength grid is refused
+    rcm.write_lbl_asc(str(d / "lbl.o3.asc"), wvl[:-1], tau5[2][:-1])
+    r = subprocess.run([exe(rcm), "--atm", lbl_atm, "--lbl", str(d), "--max-steps", "1"], capture_output=True, text=True)
+    assert r.returncode == 1 and "lbl.o3.asc" in r.stderr
+
+
 def test_driver_argument_errors(rcm, tmp_path):
     r = subprocess.run([exe(rcm), "--atm", "/no/such.atm", "--table", table_path(10)], capture_output=True, text=True)
     assert r.returncode == 1 and "rcm_rce:" in r.stderr
