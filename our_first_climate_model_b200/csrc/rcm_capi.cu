@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <functional>
@@ -417,6 +418,10 @@ int launch_part(rcm_solver* s, int mode, int nsteps, bool want_diag, const Part&
     a.cloud_col = s->has_col_cloud ? s->d_cloud_col + o : nullptr;
     int per_sm = p.sh.per_sm;
     if (rcm_step_smem_bytes(a.C, s->nactive, a.nthreads) * per_sm > 224 * 1024) per_sm = 1;
+    if (const char* e = std::getenv("RCM_CTAS_PER_SM")) {  // occupancy experiments (tools/occupancy_probe.py): fewer resident CTAs
+        const int v = std::atoi(e);
+        if (v >= 1 && v < per_sm) per_sm = v;
+    }
     const int ctas = nsm * per_sm;
     const int grid = a.ntiles < ctas ? a.ntiles : ctas;
     CU(rcm_launch_step(mode, a, s->nactive, grid, st));
