@@ -2,8 +2,8 @@
 main.cpp:214-264, batched) and its use by the step: per-column solar_irr in the heating of the lowest layer
 (main.cpp:341) and per-column grey-cloud optical depth in tau (main.cpp:266-274).
 
-Checkers: the host restatement rcm_solar_setup (bit-identical to the oracle port, which reproduces the reference's
-committed output.txt values: tests/test_host.py, tests/test_oracle.py) and the oracle port's time stepping.
+Checkers: the oracle port (oracle/rcm_oracle.c): its solar setup, which reproduces the solar lines of the reference's
+committed output.txt (tests/test_oracle.py), and its time stepping.
 """
 import os
 
@@ -37,7 +37,7 @@ def forcing(n, seed, wide=False):
     return rng.uniform(0.5, 4.0, n), rng.uniform(0.3, 0.8, n), rng.uniform(0.05, 0.3, n)
 
 
-def test_device_solar_setup_equals_host(rcm):
+def test_device_solar_setup_equals_oracle(rcm, port):
     """4,099 columns (ragged last block) with their own cloud optical depth, zenith cosine and albedo."""
     n = 4099
     pl, st, Ts = ensemble(rcm, n, 7)
@@ -47,10 +47,8 @@ def test_device_solar_setup_equals_host(rcm):
     s.set_columns(pl, st["Tlayer"], Ts, st["vmr9"], st["rel_hum"])
     got = s.set_column_solar(None, tau_s, mu_s, alb)
     ref_irr, ref_rt = np.zeros(n), np.zeros(n)
-    for c in range(n):
-        sp = rcm.default_solar_params()
-        sp.tau_s, sp.mu_s, sp.albedo = tau_s[c], mu_s[c], alb[c]
-        o = rcm.solar_setup(sp)
+    for c in range(n):  # the checker is the oracle's restatement of main.cpp:214-264 (oracle/rcm_oracle.c)
+        o = port.solar_setup(tau_s=tau_s[c], mu_s=mu_s[c], albedo=alb[c])
         ref_irr[c], ref_rt[c] = o["solar_irr"], o["r_total"]
     # same operation order, no contraction; the only library call is pow(t_dir, 2) on the host (RN square here)
     np.testing.assert_allclose(got["r_total"], ref_rt, rtol=4e-16, atol=0)
@@ -58,7 +56,8 @@ def test_device_solar_setup_equals_host(rcm):
     assert np.mean(got["solar_irr"] == ref_irr) > 0.95
     # scalars only = the reference's committed Consts: bit-identical to the value pinned by output.txt
     one = s.set_column_solar(rcm.default_solar_params())
-    assert np.all(one["solar_irr"] == rcm.solar_setup()["solar_irr"]) and np.all(one["r_total"] == rcm.solar_setup()["r_total"])
+    assert np.all(one["solar_irr"] == port.solar_setup()["solar_irr"]) and np.all(one["r_total"] == port.solar_setup()["r_total"])
+    assert f"{one['solar_irr'][0]:.6f}" == "236.882897"  # tau_s = 2.0, the committed Consts (tests/test_oracle.py)
     s.close()
 
 
