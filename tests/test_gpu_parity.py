@@ -333,6 +333,47 @@ def test_row_staging_fallback_and_equivalence(solver, rcm, port, golden):
     assert (lt.max(axis=1) - lt.min(axis=1)).max() >= 3, "the wild ensemble must exercise the fallback"
 
 
+def test_two_million_columns_index_arithmetic(rcm, golden):
+    """Maximum-size edge: 2,097,152 columns (32 x BASELINE's ensemble, 335 MB per state array, tau of 3.4 GB) on the
+    10-wavelength table - the element offsets of tau pass 2^31, the byte offsets of the state arrays 2^28.  Replicated
+    columns are bit-identical at the far end of every array, in the fused step, in the tau build and in the host-buffer
+    step (chunk pipeline), and equal the 16-column run."""
+    import gc
+    base = 16
+    rep = 131072
+    ncol = base * rep
+    s = rcm.Solver(0)
+    s.set_repwvl_table_from(rcm.Table(table_path(10)))
+    s.set_option(1, 1)  # the 16-column tile shape of big ensembles also for the 16-column run: same order of additions
+    s.set_columns(golden["plevel"], golden["Tlayer"], golden["Tsurf"], golden["vmr9"], golden["rel_hum"])
+    s.advance(2)
+    small = s.get_state()
+    tau_small, _, lt_small = s.build_tau()
+    s.set_option(1, 0)
+    tile = lambda a: np.tile(a, (rep,) + (1,) * (a.ndim - 1))
+    vmr9 = tile(golden["vmr9"])
+    s.set_columns(golden["plevel"], tile(golden["Tlayer"]), tile(golden["Tsurf"]), vmr9, tile(golden["rel_hum"]))
+    del vmr9
+    gc.collect()
+    sc = s.advance(2)
+    big = s.get_state()
+    for k in ("E_up", "E_down", "dE", "Tlayer", "Tsurf", "h2o", "dt", "time_h"):
+        b = big[k].reshape(rep, base, -1)
+        ref = small[k].reshape(base, -1)
+        assert np.array_equal(b[0], ref) and np.array_equal(b[-1], ref) and np.array_equal(b[rep // 2 + 1], ref), k
+    assert sc[-1, 2] == 0 and np.isfinite(sc).all()
+    np.testing.assert_allclose(sc[-1, 0], rep * float(np.sum(float(golden["solar_irr"]) - small["E_up"][:, 0])), rtol=1e-12)
+    del big
+    gc.collect()
+    tau, _, lt = s.build_tau()                       # [ncol][10][20] doubles = 3.4 GB: offsets beyond 2^31 elements
+    t = tau.reshape(rep, base, 10, 20)
+    assert np.array_equal(t[0], tau_small) and np.array_equal(t[-1], tau_small) and np.array_equal(t[rep - 7], tau_small)
+    assert np.array_equal(lt.reshape(rep, base, 20)[-1], lt_small)
+    del tau, t, lt
+    gc.collect()
+    s.close()
+
+
 def test_full_size_properties(solver, rcm, golden):
     """BASELINE-size ensemble (65,536 columns x 100 wavelengths): size-independent properties.
     (1) replicated columns give bit-identical results wherever they sit in the ensemble;
