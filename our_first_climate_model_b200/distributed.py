@@ -88,11 +88,11 @@ class StepScalarExchange:
         if self.work[k] is not None:
             self.work[k].wait()
             self.work[k] = None
-        self.send[k].copy_(scalars.view(-1)[-4:])
         if self.world > 1:
+            self.send[k].copy_(scalars.view(-1)[-4:])
             self.work[k] = dist.all_gather_into_tensor(self.recv[k].view(-1), self.send[k], async_op=True)
         else:
-            self.recv[k, 0].copy_(self.send[k])
+            self.recv[k, 0].copy_(scalars.view(-1)[-4:])  # one rank: the slot is the rank's own scalars
         self.count += 1
         return self.count - 1
 
