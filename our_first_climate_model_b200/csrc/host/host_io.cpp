@@ -40,9 +40,12 @@ struct H5 {
     explicit H5(const std::vector<unsigned char>& buf) : b(buf) {}
 
     bool in(uint64_t off, uint64_t n) const { return off <= b.size() && n <= b.size() - off; }
+    // every read is bounds-checked (a read outside the file yields 0): malformed files end in RCM_ERR_FORMAT
+    unsigned at(uint64_t off) const { return off < b.size() ? b[off] : 0u; }
     uint64_t u(uint64_t off, int n) const {
         uint64_t v = 0;
-        for (int i = n - 1; i >= 0; --i) v = (v << 8) | b[off + i];
+        if (!in(off, (uint64_t)n)) return 0;
+        for (int i = n - 1; i >= 0; --i) v = (v << 8) | at(off + i);
         return v;
     }
     bool sig(uint64_t off, const char* s) const { return in(off, 4) && std::memcmp(&b[off], s, 4) == 0; }
@@ -55,18 +58,18 @@ struct H5 {
 
     // One link message (version 1); returns false when `p` does not start one.
     bool link(uint64_t& p, std::string& name, uint64_t& target) const {
-        if (!in(p, 4) || b[p] != 1) return false;
-        unsigned flags = b[p + 1];
+        if (!in(p, 4) || at(p) != 1) return false;
+        unsigned flags = at(p + 1);
         uint64_t q = p + 2;
         unsigned type = 0;
-        if (flags & 0x08) type = b[q++];
+        if (flags & 0x08) type = at(q++);
         if (flags & 0x04) q += 8;
         if (flags & 0x10) q += 1;
         int w = 1 << (flags & 3);
         if (!in(q, w)) return false;
         uint64_t len = u(q, w);
         q += w;
-        if (len == 0 || !in(q, len + 8)) return false;
+        if (len == 0 || len > b.size() || !in(q, len + 8)) return false;
         name.assign((const char*)&b[q], len);
         q += len;
         target = UINT64_MAX;
@@ -83,20 +86,20 @@ struct H5 {
     void messages(uint64_t p, uint64_t end, bool tracked, Dataset& d, std::map<std::string, uint64_t>& links,
                   int depth) const {
         while (p + 4 <= end && in(p, 4)) {
-            unsigned type = b[p];
+            unsigned type = at(p);
             uint64_t size = u(p + 1, 2);
             uint64_t body = p + 4 + (tracked ? 2 : 0);
             if (!in(body, size)) return;
             if (type == 0x01) {  // dataspace
-                unsigned ver = b[body], rank = b[body + 1];
+                unsigned ver = at(body), rank = at(body + 1);
                 uint64_t q = body + (ver == 2 ? 4 : 8);
                 d.shape.clear();
                 for (unsigned i = 0; i < rank && in(q, 8); ++i, q += 8) d.shape.push_back(u(q, 8));
             } else if (type == 0x03) {  // datatype: class 1 = IEEE float, bit0 of the class bits = big endian
-                unsigned cls = b[body] & 0x0F, bits0 = b[body + 1];
+                unsigned cls = at(body) & 0x0F, bits0 = at(body + 1);
                 d.f64le = (cls == 1 && u(body + 4, 4) == 8 && (bits0 & 1) == 0);
             } else if (type == 0x08) {  // layout: version 3, class 1 = contiguous
-                if (b[body] == 3 && b[body + 1] == 1) {
+                if (at(body) == 3 && at(body + 1) == 1) {
                     d.addr = u(body + 2, 8);
                     d.size = u(body + 10, 8);
                 }
@@ -113,8 +116,8 @@ struct H5 {
     }
 
     bool object(uint64_t addr, Dataset& d, std::map<std::string, uint64_t>& links) const {
-        if (!sig(addr, "OHDR") || b[addr + 4] != 2) return false;
-        unsigned flags = b[addr + 5];
+        if (!sig(addr, "OHDR") || at(addr + 4) != 2) return false;
+        unsigned flags = at(addr + 5);
         uint64_t p = addr + 6;
         if (flags & 0x20) p += 16;
         if (flags & 0x10) p += 4;
@@ -130,14 +133,14 @@ struct H5 {
     // direct blocks of every fractal heap.
     void heap_links(std::map<std::string, uint64_t>& links) const {
         for (uint64_t h = 0; h + 4 <= b.size(); ++h) {
-            if (!sig(h, "FRHP") || b[h + 4] != 0) continue;
-            unsigned hflags = b[h + 9];
+            if (!sig(h, "FRHP") || at(h + 4) != 0) continue;
+            unsigned hflags = at(h + 9);
             // fixed part of the heap header up to "maximum heap size" (bits)
             uint64_t maxbits_off = h + 4 + 1 + 2 + 2 + 1 + 4 + 8 * 12 + 2 + 8 + 8;
             if (!in(maxbits_off, 2)) continue;
             uint64_t off_bytes = (u(maxbits_off, 2) + 7) / 8;
             for (uint64_t d = 0; d + 4 <= b.size(); ++d) {
-                if (!sig(d, "FHDB") || b[d + 4] != 0 || u(d + 5, 8) != h) continue;
+                if (!sig(d, "FHDB") || at(d + 4) != 0 || u(d + 5, 8) != h) continue;
                 uint64_t p = d + 5 + 8 + off_bytes + ((hflags & 0x02) ? 4 : 0);
                 std::string nm;
                 uint64_t tgt;
@@ -373,7 +376,7 @@ int rcm_write_profiles(const char* path, int append, int header, int ncol, const
     if (!f) return RCM_ERR_IO;
     std::string out;
     out.reserve(1 << 20);
-    char row[160];
+    char row[1600];  // "%f" of a diverged temperature (1e300) is over 300 characters: four of them still fit
     bool ok = true;
     if (header) out += column_ids ? "column,layer,player,Tlayer,theta,time\n" : "layer,player,Tlayer,theta,time\n";
     for (int c = 0; c < ncol && ok; ++c) {
@@ -382,8 +385,12 @@ int rcm_write_profiles(const char* path, int append, int header, int ncol, const
             const double theta = T[l] * conv[l];  // t_to_theta, main.cpp:125
             int n = 0;
             if (column_ids) n = std::snprintf(row, sizeof(row), "%d,", c);
-            n += std::snprintf(row + n, sizeof(row) - n, "%d,%f,%f,%f,%f\n", l, player[l], T[l], theta, (double)time_h[c]);
-            out.append(row, (size_t)n);
+            const int m = std::snprintf(row + n, sizeof(row) - n, "%d,%f,%f,%f,%f\n", l, player[l], T[l], theta, (double)time_h[c]);
+            if (n < 0 || m < 0 || (size_t)(n + m) >= sizeof(row)) {  // cannot happen with finite doubles; never read past `row`
+                ok = false;
+                break;
+            }
+            out.append(row, (size_t)(n + m));
         }
         if (out.size() > (1u << 20) - 4096) {
             ok = std::fwrite(out.data(), 1, out.size(), f) == out.size();

@@ -47,6 +47,7 @@ struct rcm_solver {
     double *d_Ed = nullptr, *d_Eu = nullptr, *d_dE = nullptr, *d_dt = nullptr;
     double *d_diag = nullptr, *d_scalars = nullptr, *d_tau = nullptr, *d_red = nullptr;
     int* d_lowpos = nullptr;
+    unsigned* d_ticket = nullptr;  // [diag_steps] ticket counters of rcm_reduce_diag_kernel
     double *d_solar_col = nullptr, *d_cloud_col = nullptr;  // per-column solar forcing / cloud tau (rcm_set_column_solar)
     bool has_col_solar = false, has_col_cloud = false;
     size_t diag_steps = 0, tau_cap = 0;
@@ -328,7 +329,8 @@ int ensure_diag(rcm_solver* s, int nsteps) {
     CU(dalloc(s->d_diag, (size_t)nsteps * s->cap * 4));
     CU(dalloc(s->d_scalars, (size_t)nsteps * 4));
     CU(dalloc(s->d_red, rcm_reduce_scratch_doubles(nsteps)));
-    CU(cudaMemsetAsync(s->d_red, 0, rcm_reduce_scratch_doubles(nsteps) * sizeof(double), s->stream));
+    CU(dalloc(s->d_ticket, (size_t)nsteps));  // one ticket counter per step of the capacity; every reduce launch leaves them at 0
+    CU(cudaMemsetAsync(s->d_ticket, 0, (size_t)nsteps * sizeof(unsigned), s->stream));
     s->diag_steps = nsteps;
     return RCM_OK;
 }
@@ -515,7 +517,7 @@ int rcm_destroy(rcm_solver* s) {
     void* ptrs[] = {s->d_xsec_file, s->d_coef, s->d_species, s->d_planck_c, s->d_planck_k, s->d_exp_tab, s->d_T, s->d_Ts, s->d_vmr, s->d_rh,
                     s->d_Tprev, s->d_time, s->d_lbl_lo, s->d_lbl_hi, s->d_lbl_tau5, s->d_lbl_h2o_ref, s->d_lbl_o3_ref, s->d_sH, s->d_sO,
                     s->d_dTstat, s->d_part, s->d_Ed, s->d_Eu, s->d_dE, s->d_dt, s->d_diag, s->d_scalars, s->d_red, s->d_tau,
-                    s->d_lowpos, s->d_solar_col, s->d_cloud_col};
+                    s->d_lowpos, s->d_solar_col, s->d_cloud_col, s->d_ticket};
     for (void* q : ptrs)
         if (q) cudaFree(q);
     for (auto& e : s->ev_free) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -683,6 +685,13 @@ int rcm_set_lbl_tables(rcm_solver* s, const double* wvl, const double* tau5, int
     s->lbl_nwvl = nwvl;
     s->lbl_co2_factor = co2_factor;
     s->lbl_mode = true;
+    // dc.nwvl now counts LBL wavelengths: the repwvl table / spectral grid on the device (d_coef, d_planck_*) are sized
+    // for another grid and must not be used with it - they have to be set again to go back to the repwvl path
+    if (s->dc.nwvl != nwvl) {
+        s->has_table = s->has_spectral = false;
+        s->tau_cap = 0;
+    }
+    s->tau_valid = false;
     s->dc.nwvl = nwvl;
     s->const_dirty = true;
     s->part_cap = 0;
@@ -799,6 +808,7 @@ int rcm_set_step_index(rcm_solver* s, long step_index) {
 
 int rcm_build_tau(rcm_solver* s, double* tau_out, int* lowpos_p, int* lowpos_t) {
     if (!s) return RCM_ERR_ARG;
+    if (s->lbl_mode) return fail(s, RCM_ERR_STATE, "rcm_build_tau is the repwvl read_tau: set a repwvl table after rcm_set_lbl_tables");
     if (!s->has_table || s->ncol <= 0) return fail(s, RCM_ERR_STATE, "table and columns must be loaded");
     CU(cudaSetDevice(s->device));
     int st = ensure_tau(s);
@@ -820,6 +830,7 @@ int rcm_build_tau(rcm_solver* s, double* tau_out, int* lowpos_p, int* lowpos_t) 
 
 int rcm_radiative_transfer(rcm_solver* s, const double* tau, double* E_down, double* E_up, double* dE) {
     if (!s) return RCM_ERR_ARG;
+    if (s->lbl_mode) return fail(s, RCM_ERR_STATE, "rcm_radiative_transfer needs a repwvl spectral grid: set one after rcm_set_lbl_tables");
     if (!s->has_spectral || s->ncol <= 0) return fail(s, RCM_ERR_STATE, "spectral grid and columns must be loaded");
     CU(cudaSetDevice(s->device));
     int st = ensure_tau(s);
@@ -901,7 +912,7 @@ int rcm_advance_async(rcm_solver* s, int nsteps, double** d_scalars) {
     if (s->lbl_mode) {
         st = lbl_advance(s, nsteps);
         if (st != RCM_OK) return st;
-        CU(rcm_launch_reduce_diag(s->d_diag, nsteps, s->ncol, s->p.dT_converged, s->d_red, s->d_scalars, s->stream));
+        CU(rcm_launch_reduce_diag(s->d_diag, nsteps, s->ncol, s->p.dT_converged, s->d_red, s->d_ticket, s->d_scalars, s->stream));
         s->launches += 1;
         s->step_index += nsteps;
         if (d_scalars) *d_scalars = s->d_scalars;
@@ -909,7 +920,7 @@ int rcm_advance_async(rcm_solver* s, int nsteps, double** d_scalars) {
     }
     st = launch(s, MODE_STEP, nsteps, true);
     if (st != RCM_OK) return st;
-    CU(rcm_launch_reduce_diag(s->d_diag, nsteps, s->ncol, s->p.dT_converged, s->d_red, s->d_scalars, s->stream));
+    CU(rcm_launch_reduce_diag(s->d_diag, nsteps, s->ncol, s->p.dT_converged, s->d_red, s->d_ticket, s->d_scalars, s->stream));
     s->launches += 1;
     s->step_index += nsteps;
     s->tau_valid = false;
@@ -971,7 +982,7 @@ int rcm_get_state(rcm_solver* s, double* Tlayer, double* Tsurf, double* h2o, flo
 // ------------------------------------------------------------------------------------------
 // Checkpoint / restart of an ensemble.  One flat little-endian file:
 //   "RCMCKPT1", header (int64: ncol, nactive, species_mask, step_index, has_col_solar, has_col_cloud, lbl_mode,
-//   reserved), plevel[21], then per column arrays in the order of kCkptArrays below.
+//   nwvl of the table the run used - 0 in files written before it was recorded), plevel[21], then per column arrays in the order of kCkptArrays below.
 // Everything the step reads or carries is in it, so a solver that loads the same table and this file continues
 // bit-identically (tests/test_gpu_checkpoint.py).  Tables are not stored: they are inputs of the run, not state.
 // ------------------------------------------------------------------------------------------
@@ -1007,7 +1018,7 @@ int rcm_save_checkpoint(rcm_solver* s, const char* path) {
     FILE* f = std::fopen(path, "wb");
     if (!f) return fail(s, RCM_ERR_IO, std::string("cannot write ") + path);
     const long long hdr[8] = {s->ncol, s->nactive, (long long)s->p.species_mask, s->step_index, s->has_col_solar ? 1 : 0,
-                              s->has_col_cloud ? 1 : 0, s->lbl_mode ? 1 : 0, 0};
+                              s->has_col_cloud ? 1 : 0, s->lbl_mode ? 1 : 0, s->dc.nwvl};
     bool ok = std::fwrite("RCMCKPT1", 1, 8, f) == 8 && std::fwrite(hdr, sizeof(hdr), 1, f) == 1 &&
               std::fwrite(s->plevel, sizeof(s->plevel), 1, f) == 1;
     CkptArray arr[12];
@@ -1029,6 +1040,7 @@ int rcm_save_checkpoint(rcm_solver* s, const char* path) {
 int rcm_load_checkpoint(rcm_solver* s, const char* path) {
     if (!s || !path) return RCM_ERR_ARG;
     CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->stream));  // work queued earlier may still read or write the arrays overwritten below
     FILE* f = std::fopen(path, "rb");
     if (!f) return fail(s, RCM_ERR_IO, std::string("cannot read ") + path);
     char magic[8];
@@ -1047,6 +1059,10 @@ int rcm_load_checkpoint(rcm_solver* s, const char* path) {
     if ((hdr[6] != 0) != s->lbl_mode) {
         std::fclose(f);
         return fail(s, RCM_ERR_STATE, "checkpoint belongs to the other spectral path (repwvl / line-by-line)");
+    }
+    if (hdr[7] != 0 && (s->has_table || s->lbl_mode) && hdr[7] != s->dc.nwvl) {
+        std::fclose(f);
+        return fail(s, RCM_ERR_STATE, "checkpoint was written with a table of another wavelength count");
     }
     int st = ensure_columns(s, (int)hdr[0]);
     if (st != RCM_OK) {
@@ -1151,7 +1167,7 @@ int rcm_step_host(rcm_solver* s, const double* Tlayer_in, const double* Tsurf_in
         CU(cudaEventRecord(s->pipe_done[i], s->pipe_stream[i]));
         CU(cudaStreamWaitEvent(s->stream, s->pipe_done[i], 0));
     }
-    CU(rcm_launch_reduce_diag(s->d_diag, 1, s->ncol, s->p.dT_converged, s->d_red, s->d_scalars, s->stream));
+    CU(rcm_launch_reduce_diag(s->d_diag, 1, s->ncol, s->p.dT_converged, s->d_red, s->d_ticket, s->d_scalars, s->stream));
     s->launches += 1;
     s->step_index += 1;
     s->tau_valid = false;

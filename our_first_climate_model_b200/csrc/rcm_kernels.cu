@@ -272,12 +272,13 @@ cudaError_t rcm_launch_step(int mode, const StepArgs& a, int nactive, int grid, 
     return cudaErrorInvalidValue;
 }
 
-size_t rcm_reduce_scratch_doubles(int nsteps) { return (size_t)nsteps * (RED_BLOCKS * 4 + 1); }
+size_t rcm_reduce_scratch_doubles(int nsteps) { return (size_t)nsteps * RED_BLOCKS * 4; }
 
-// scratch: rcm_reduce_scratch_doubles(nsteps) doubles, zeroed once when allocated (the tickets live at its end)
+// scratch: rcm_reduce_scratch_doubles(capacity) doubles; ticket: one counter per step of the CAPACITY the buffers were
+// allocated for, zeroed once at allocation (every launch leaves its counters at zero again).  The counters have their
+// own allocation: placed behind the partials of the current nsteps they aliased the partials of an earlier, longer call.
 cudaError_t rcm_launch_reduce_diag(const double* diag, int nsteps, int ncol, double dT_converged, double* scratch,
-                                   double* scalars, cudaStream_t st) {
-    unsigned* ticket = reinterpret_cast<unsigned*>(scratch + (size_t)nsteps * RED_BLOCKS * 4);
+                                   unsigned* ticket, double* scalars, cudaStream_t st) {
     rcm_reduce_diag_kernel<<<dim3(RED_BLOCKS, nsteps), RED_THREADS, 0, st>>>(diag, ncol, dT_converged, scratch, ticket, scalars);
     return cudaGetLastError();
 }

@@ -127,7 +127,7 @@ cudaError_t rcm_upload_const(const DevConst& c);
 cudaError_t rcm_launch_step(int mode, const StepArgs& a, int nactive, int grid, cudaStream_t st);
 size_t rcm_reduce_scratch_doubles(int nsteps);
 cudaError_t rcm_launch_reduce_diag(const double* diag, int nsteps, int ncol, double dT_converged, double* scratch,
-                                   double* scalars, cudaStream_t st);
+                                   unsigned* ticket, double* scalars, cudaStream_t st);
 cudaError_t rcm_launch_coef(const double* xsec_file, double* coef, int nt, int ns, int nw, int np, int nact,
                             const int* d_species, cudaStream_t st);
 cudaError_t rcm_launch_microbench(int which, double* out, const double* tab, long iters, int grid,

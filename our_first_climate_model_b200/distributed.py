@@ -64,6 +64,16 @@ def allreduce_step_scalars(t: torch.Tensor) -> torch.Tensor:
     return t
 
 
+def require_shared_stream(solver) -> None:
+    """The scalars are read by torch / NCCL on torch's current stream: the solver must queue its kernels on that very
+    stream (rcm_set_stream), otherwise the copy races the reduce kernel and stale scalars travel."""
+    if solver is None or not torch.cuda.is_available():
+        return
+    if getattr(solver, "stream_ptr", None) != torch.cuda.current_stream().cuda_stream:
+        raise RuntimeError("call solver.set_stream(s.cuda_stream) with a torch.cuda.Stream s that is torch's current "
+                           "stream (the legacy default stream cannot be shared with the solver)")
+
+
 class StepScalarExchange:
     """The per-step collective without a per-step stall.
 
@@ -72,9 +82,11 @@ class StepScalarExchange:
     queued, so the next step's kernel starts immediately.  Sums and maxima over the ranks are taken from the gathered
     rows when somebody looks (`result(k)`, `latest()`): the decision "is the ensemble stationary" needs them every
     few hundred steps, not every step.  A slot is reused only after its collective has completed.
-    With one rank (or no process group) it just keeps references to the local scalars."""
+    With one rank (or no process group) it just keeps references to the local scalars.
+    `solver`: when given, every submit() checks that the solver launches on torch's current stream."""
 
-    def __init__(self, device, ring: int = 8):
+    def __init__(self, device, ring: int = 8, solver=None):
+        self.solver = solver
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.ring = ring
         self.send = torch.zeros(ring, 4, dtype=torch.float64, device=device)
@@ -84,6 +96,7 @@ class StepScalarExchange:
 
     def submit(self, scalars: torch.Tensor) -> int:
         """scalars: float64[4] (layout of rcm_step_scalars) of the step just queued. Returns the step's ticket."""
+        require_shared_stream(self.solver)
         k = self.count % self.ring
         if self.work[k] is not None:
             self.work[k].wait()
@@ -140,10 +153,7 @@ def run_to_equilibrium(solver, ncol_total: int, max_steps: int, check_every: int
     (one launch per block, nothing crosses GPUs meanwhile); after each block ONE allreduce of the block's scalars
     decides - identically on every rank - whether the whole ensemble is stationary (n_converged == ncol_total).
     With one rank this is rcm_run_to_equilibrium."""
-    if torch.cuda.is_available() and getattr(solver, "stream_ptr", None) != torch.cuda.current_stream().cuda_stream:
-        # the scalars are reduced by torch / NCCL on torch's current stream: the kernels must be queued on the same one
-        raise RuntimeError("run_to_equilibrium: call solver.set_stream(s.cuda_stream) with a torch.cuda.Stream s that is "
-                           "torch's current stream (the legacy default stream cannot be shared with the solver)")
+    require_shared_stream(solver)
     done = 0
     means = None
     while done < max_steps:

@@ -37,3 +37,32 @@ def test_relinked_reference_driver_runs_on_the_gpu(exe, golden, tmp_path):
         assert len(olr) == 2                                            # iterations i = 0 and 1
         assert abs(olr[0] - golden["s1_E_up_100"][0, 0]) < 1e-10 * olr[0]
         assert abs(olr[1] - golden["s5_trace_100"][0, 1, 22]) < 1e-9 * olr[1]
+
+
+@pytest.mark.parametrize("prop_at_lev", [1, 0])
+@pytest.mark.parametrize("n", [20, 100])
+def test_read_tau_adapter_against_the_reference_build(prop_at_lev, n, golden, tmp_path):
+    """One caller of read_tau (oracle/read_tau_cli.cpp, includes the reference's repwvl_thermal.h) linked against the
+    reference's repwvl_thermal.cpp and against librcm_b200.so: bit-identical tau, wvl and weight - also for prop_at_Lev != 0
+    (repwvl_thermal.cpp:219-224: T and VMRs given at the 21 levels), which the reference driver never uses."""
+    ref, mine = (os.path.join(BIN, f"read_tau_cli_{k}") for k in ("ref", "b200"))
+    if not (os.path.exists(ref) and os.path.exists(mine)):
+        pytest.skip("read_tau_cli not built (needs /root/reference at build time)")
+    rng = np.random.default_rng(7 + n)
+    c = 3  # a perturbed member
+    T = golden["Tlevel"][c] + rng.uniform(-4, 4, 21)
+    vmr = np.zeros((9, 21))
+    for k, row in zip((0, 2, 1, 5, 3), golden["vmr_ppm_level"][c]):  # file order H2O, O3, CO2, CH4, N2O -> read_tau's argument order
+        vmr[k] = row * 1e-6
+    with open(tmp_path / "in.bin", "wb") as f:
+        f.write(np.ascontiguousarray(golden["plevel"], dtype="<f8").tobytes() + T.astype("<f8").tobytes() + vmr.astype("<f8").tobytes())
+    table = os.path.join(GOLDEN, f"Reduced{n}Forcing.rcmtab")
+    out = {}
+    for k, exe in (("ref", ref), ("mine", mine)):
+        r = subprocess.run([exe, table, str(tmp_path / "in.bin"), str(tmp_path / f"{k}.bin"), str(prop_at_lev)],
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, (k, r.returncode, r.stderr)
+        out[k] = (tmp_path / f"{k}.bin").read_bytes()
+    nw = int(np.frombuffer(out["ref"][:4], dtype="<i4")[0])
+    assert nw == n and len(out["ref"]) == 4 + 8 * (nw * 20 + 2 * nw)
+    assert out["mine"] == out["ref"]

@@ -1,0 +1,80 @@
+"""Regression tests for defects found in review (ADVICE.md of round 1)."""
+import numpy as np
+import pytest
+
+from conftest import table_path
+
+pytestmark = pytest.mark.gpu
+
+
+def _load(s, rcm, golden, n=20, sl=slice(0, 5)):
+    s.set_repwvl_table_from(rcm.Table(table_path(n)))
+    s.set_columns(golden["plevel"], golden["Tlayer"][sl], golden["Tsurf"][sl], golden["vmr9"][sl], golden["rel_hum"][sl])
+
+
+def test_scalars_after_a_longer_call(rcm, golden):
+    """advance(8) then advance(3) on the same solver: the ticket counters of the scalar reduction used to sit behind the
+    partials of the CURRENT nsteps and aliased partials left by the longer call - no CTA was 'last', the scalars of
+    the short call were never written.  Compare with a fresh solver that only ever ran 3 steps at a time."""
+    a, b = rcm.Solver(0), rcm.Solver(0)
+    try:
+        _load(a, rcm, golden)
+        a.advance(8)
+        sa = a.advance(3)
+        sa1 = a.advance(1)
+        _load(b, rcm, golden)
+        for _ in range(2):
+            b.advance(3)
+        b.advance(2)
+        sb = b.advance(3)
+        sb1 = b.advance(1)
+        assert np.array_equal(sa, sb) and np.array_equal(sa1, sb1)
+        assert np.all(sa[:, 3] > 0)  # max|dE| of a real step is never 0
+        # ... and the C driver with a short last block (max_steps % check_every != 0) decides on fresh scalars
+        _load(a, rcm, golden)
+        done, last = a.run_to_equilibrium(11, 8)
+        _load(b, rcm, golden)
+        ref = b.advance(11)
+        assert done == 11 and np.array_equal(last, ref[-1])
+    finally:
+        a.close()
+        b.close()
+
+
+def test_lbl_tables_invalidate_the_repwvl_grid(rcm, golden):
+    """rcm_set_lbl_tables re-sizes the wavelength axis: the repwvl-only entry points must refuse to run on the device
+    arrays of the old grid (they used to launch over LBL nwvl with buffers sized for the repwvl table)."""
+    s = rcm.Solver(0)
+    try:
+        _load(s, rcm, golden)
+        s.build_tau()
+        atm_h2o = golden["vmr9"][0, 0]
+        wvl, tau5 = rcm.make_lbl_tables(300, 5, golden["plevel"], atm_h2o, golden["vmr9"][0, 2])
+        s.set_lbl_tables(wvl, tau5, atm_h2o, None, 1.0)
+        with pytest.raises(rcm.RcmError):
+            s.build_tau()
+        with pytest.raises(rcm.RcmError):
+            s.radiative_transfer(np.zeros((5, 300, 20)))
+        s.advance(1)  # the LBL step itself works
+        _load(s, rcm, golden)  # and a repwvl table brings the repwvl path back
+        tau, _, _ = s.build_tau()
+        assert np.array_equal(tau, golden["tau20"][:5])
+    finally:
+        s.close()
+
+
+def test_checkpoint_refuses_another_wavelength_count(rcm, golden, tmp_path):
+    s = rcm.Solver(0)
+    try:
+        _load(s, rcm, golden, 20)
+        s.advance(2)
+        path = str(tmp_path / "c.ckpt")
+        s.save_checkpoint(path)
+        s.set_repwvl_table_from(rcm.Table(table_path(10)))
+        with pytest.raises(rcm.RcmError):
+            s.load_checkpoint(path)
+        s.set_repwvl_table_from(rcm.Table(table_path(20)))
+        s.load_checkpoint(path)
+        s.advance(1)
+    finally:
+        s.close()

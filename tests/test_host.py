@@ -200,3 +200,71 @@ def test_write_profiles_reproduces_reference_output_rows(rcm, golden, tmp_path):
     assert lines[1 + 20 * c + l] == "%d,%d,%f,%f,%f,%f" % (c, l, player, T[c, l], T[c, l] * conv, float(c))
     with pytest.raises(rcm.RcmError):
         rcm.write_profiles(str(tmp_path / "no_such_dir" / "x.txt"), golden["plevel"], st["Tlayer"], 0.0)
+
+
+# ---- exact-signature boundary of the line-by-line side (include/rcm_b200_adapters.hpp) ------------------
+BIN = os.path.join(ROOT, "oracle", "_ref")
+
+
+def _needs_bin(name):
+    path = os.path.join(BIN, name)
+    if not os.path.exists(path):
+        pytest.skip(f"{name} not built (needs /root/reference at build time)")
+    return path
+
+
+def test_unmodified_testlblarts_links_against_the_product_library(rcm, tmp_path):
+    """The reference's only caller of ASCII_file2xy2D (lbl.arts/testlblarts.cpp:13-38), compiled UNMODIFIED and linked
+    against librcm_b200.so instead of lbl.arts/ascii.cpp, reads a table in the README's format."""
+    exe = _needs_bin("testlblarts_b200")
+    nw = 321
+    os.makedirs(tmp_path / "lbl.arts")
+    wvl = np.linspace(4000.0, 1e5, nw)
+    tau = np.random.default_rng(0).uniform(0, 3, (nw, 20))
+    rcm.write_lbl_asc(str(tmp_path / "lbl.arts" / "lbl.co2.asc"), wvl, tau)
+    r = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stderr
+    assert f" ... read {nw} wavelengths and 20 layers from ./lbl.arts/lbl.co2.asc" in r.stderr   # testlblarts.cpp:32-33
+    os.remove(tmp_path / "lbl.arts" / "lbl.co2.asc")
+    r = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=60)
+    assert r.returncode == 255 and "Error -1 reading ./lbl.arts/lbl.co2.asc" in r.stderr          # ASCIIFILE_NOT_FOUND
+
+
+def test_ascii_file2xy2D_exact_signature_and_ownership(rcm, tmp_path):
+    """extern "C" int ASCII_file2xy2D(char*, int*, int*, double**, double***) (ascii.h:63): x is one calloc'ed vector, y an
+    array of nx calloc'ed rows released by ASCII_free_double(y, nx) (ascii.cpp:955-965, :1612-1613)."""
+    lib = rcm.load_library()
+    p = _write(tmp_path / "t.asc", "# c\n1 10 20 30\n2 11 21 31\n\n3 12 22 x\n")
+    nx, ny = ctypes.c_int(0), ctypes.c_int(0)
+    x = ctypes.POINTER(ctypes.c_double)()
+    y = ctypes.POINTER(ctypes.POINTER(ctypes.c_double))()
+    st = lib.ASCII_file2xy2D(ctypes.c_char_p(p.encode()), ctypes.byref(nx), ctypes.byref(ny), ctypes.byref(x), ctypes.byref(y))
+    assert st == 0 and (nx.value, ny.value) == (3, 3)
+    assert [x[i] for i in range(3)] == [1.0, 2.0, 3.0]
+    assert [[y[i][j] for j in range(3)] for i in range(3)] == [[10, 20, 30], [11, 21, 31], [12, 22, 0]]
+    assert lib.ASCII_free_double(y, nx) == 0
+    ctypes.CDLL(None).free(x)
+    for bad, code in (("1 2 3\n4 5\n", -5), ("", -5)):
+        assert lib.ASCII_file2xy2D(_write(tmp_path / "b.asc", bad).encode(), ctypes.byref(nx), ctypes.byref(ny),
+                                   ctypes.byref(x), ctypes.byref(y)) == code
+    assert lib.ASCII_file2xy2D(str(tmp_path / "missing").encode(), ctypes.byref(nx), ctypes.byref(ny), ctypes.byref(x),
+                               ctypes.byref(y)) == -1
+
+
+def test_cplkavg_exact_signature_against_the_reference_build(golden_misc):
+    """double cplkavg(double, double, double) (cplkavg.h:7): one caller (oracle/cplkavg_cli.cpp, includes the reference's
+    header) linked against the reference's cplkavg.cpp and against librcm_b200.so gives the same numbers; bad arguments
+    end the process with the reference's message and exit status (cplkavg.cpp:144-146, :32-35)."""
+    ref, mine = _needs_bin("cplkavg_cli_ref"), _needs_bin("cplkavg_cli_b200")
+    m = golden_misc
+    inp = "".join(f"{a!r} {b!r} {t!r}\n" for a, b, t in zip(m["cpl_lo"].tolist(), m["cpl_hi"].tolist(), m["cpl_T"].tolist()))
+    out = {}
+    for k, exe in (("ref", ref), ("mine", mine)):
+        r = subprocess.run([exe], input=inp, capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stderr
+        out[k] = np.array([float(v) for v in r.stdout.split()])
+    assert out["ref"].shape == m["cpl_val"].shape and np.array_equal(out["ref"], m["cpl_val"])
+    assert np.array_equal(out["mine"], out["ref"])
+    for exe in (ref, mine):
+        r = subprocess.run([exe], input="500 400 300\n", capture_output=True, text=True, timeout=60)
+        assert r.returncode == 1 and "planck_func1--temperature or wavenums. wrong" in r.stderr
