@@ -428,11 +428,12 @@ class Solver:
         _check(_lib.rcm_step_host(self._h, *[C.c_void_p(x) for x in (T_in, Ts_in, vmr_in, Ed, Eu, dE, T_out, Ts_out)]),
                self._h)
 
-    def step_host(self, Tlayer, Tsurf, vmr_active) -> dict:
+    def step_host(self, Tlayer, Tsurf, vmr_active=None) -> dict:
         """rcm_step_host with numpy arrays: upload T / Tsurf / active VMRs, one step, download the results."""
         n = self.ncol
-        T, Ts, v = _f64(Tlayer), _f64(Tsurf), _f64(vmr_active)
-        assert T.shape == (n, NLAY) and Ts.shape == (n,) and v.shape == (n, self.nactive, NLAY)
+        T, Ts = _f64(Tlayer), _f64(Tsurf)
+        v = None if vmr_active is None else _f64(vmr_active)  # None: the VMRs on the device stay (H2O follows the feedback)
+        assert T.shape == (n, NLAY) and Ts.shape == (n,) and (v is None or v.shape == (n, self.nactive, NLAY))
         out = dict(E_down=np.zeros((n, NLEV)), E_up=np.zeros((n, NLEV)), dE=np.zeros((n, NLAY)),
                    Tlayer=np.zeros((n, NLAY)), Tsurf=np.zeros(n))
         _check(_lib.rcm_step_host(self._h, _p(T), _p(Ts), _p(v), _p(out["E_down"]), _p(out["E_up"]), _p(out["dE"]),

@@ -28,6 +28,7 @@ struct rcm_solver {
     int opt_config = 0;        // 0: planned (plan_parts); k > 0: force kShapes[k-1] for the whole ensemble
         // prepare the next wavelength inside the angle loop (0: separate phase)
     int opt_stage_rows = 1;    // K1 reads its table rows from shared memory, staged one wavelength ahead
+    int opt_path = 0;          // 0: split path (tile x wavelength-split units) when it applies; 1: fused tile kernel
     int opt_cplk_narrow = 0;   // rcm_cplkavg_device evaluates the LBL kernel's narrow-band variant (tests)
     double tau_clamp = 240.0;  // set by build_angles
     int clampk = 1;
@@ -61,12 +62,22 @@ struct rcm_solver {
     double *d_lbl_lo = nullptr, *d_lbl_hi = nullptr, *d_lbl_tau5 = nullptr, *d_lbl_h2o_ref = nullptr,
            *d_lbl_o3_ref = nullptr, *d_sH = nullptr, *d_sO = nullptr, *d_dTstat = nullptr, *d_part = nullptr;
     size_t part_cap = 0;
+    // split path (rcm_split_kernels.cuh)
+    unsigned char* d_tile = nullptr;    // [tiles][TILE_BYTES]
+    double* d_spart = nullptr;          // [tiles][nsplit][42][16]
+    unsigned* d_counter = nullptr;      // [4] work counters: the solver's stream and the three pipeline streams
+    size_t tile_cap = 0, spart_cap = 0;
+    bool tile_vmr_valid = false;        // the constant species' rows of the tile blocks are current
     std::vector<double> stage;  // host packing buffer
     std::string err;
     long launches = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_free, ev_used;
     cudaStream_t pipe_stream[3] = {nullptr, nullptr, nullptr};  // rcm_step_host's chunk pipeline
     cudaEvent_t pipe_done[3] = {nullptr, nullptr, nullptr}, pipe_start = nullptr;
+    // ... of the split path: uploads + K5 prep (high priority), unit kernels alternating on two streams, K5 finish + downloads
+    // (high priority); one event per chunk and stage
+    cudaStream_t sp_up = nullptr, sp_rt[2] = {nullptr, nullptr}, sp_down = nullptr;
+    cudaEvent_t sp_prep[8] = {}, sp_rtdone[8] = {}, sp_end = nullptr;
     double kt_ms = 0.0;
     long kt_n = 0;
 };
@@ -316,6 +327,10 @@ int ensure_columns(rcm_solver* s, int ncol) {
     s->cap = ncol;
     s->diag_steps = 0;
     s->part_cap = 0;
+    s->tile_cap = s->spart_cap = 0;
+    s->tile_vmr_valid = false;
+    if (s->d_dTstat) cudaFree(s->d_dTstat);
+    s->d_dTstat = nullptr;
     // the per-column forcing buffers follow the capacity: reallocated by the next rcm_set_column_solar / checkpoint load
     if (s->d_solar_col) cudaFree(s->d_solar_col);
     if (s->d_cloud_col) cudaFree(s->d_cloud_col);
@@ -431,6 +446,150 @@ int launch_part(rcm_solver* s, int mode, int nsteps, bool want_diag, const Part&
     return RCM_OK;
 }
 
+
+// ---- split path: (tile, wavelength split) units, two kernels per step (rcm_split_kernels.cuh) ----------------------
+bool use_split(const rcm_solver* s) {
+    return !s->lbl_mode && s->has_table && s->nactive == 5 && s->opt_config == 0 && s->opt_path == 0;
+}
+
+struct SplitGeom { int ntiles, nitem, nsplit; };
+SplitGeom split_geom(const rcm_solver* s, int ncols) {
+    SplitGeom g;
+    g.ntiles = (ncols + 15) / 16;
+    g.nitem = (s->dc.nwvl + 3) / 4;
+    g.nsplit = (g.nitem + rcm_split_ipu() - 1) / rcm_split_ipu();
+    return g;
+}
+
+int ensure_split(rcm_solver* s) {
+    const SplitGeom g = split_geom(s, s->cap);
+    const size_t tiles = (size_t)g.ntiles, need_part = tiles * g.nsplit * rcm_split_part_doubles();
+    if (tiles > s->tile_cap || !s->d_tile) {
+        CU(dalloc(s->d_tile, tiles * rcm_split_tile_bytes()));
+        s->tile_cap = tiles;
+        s->tile_vmr_valid = false;
+    }
+    if (need_part > s->spart_cap || !s->d_spart) {
+        CU(dalloc(s->d_spart, need_part));
+        s->spart_cap = need_part;
+    }
+    if (!s->d_dTstat) CU(dalloc(s->d_dTstat, (size_t)s->cap));
+    if (!s->d_counter) {
+        CU(dalloc(s->d_counter, (size_t)4));
+        CU(cudaMemsetAsync(s->d_counter, 0, 4 * sizeof(unsigned), s->stream));
+    }
+    return RCM_OK;
+}
+
+// arguments for the columns [col0, col0 + ncols) (col0 a multiple of 16), work counter `which`
+SplitArgs split_args(rcm_solver* s, int col0, int ncols, int which) {
+    const SplitGeom g = split_geom(s, ncols);
+    const size_t o = (size_t)col0, t0 = o / 16;
+    SplitArgs a{};
+    a.ncol = ncols;
+    a.diag_ncol = s->ncol;
+    a.ntiles = g.ntiles;
+    a.nsplit = g.nsplit;
+    a.ipu = rcm_split_ipu();
+    a.nitem = g.nitem;
+    a.nunits = g.ntiles * g.nsplit;
+    a.stage_rows = s->opt_stage_rows;
+    a.clampk = s->clampk;
+    a.h2o_slot = s->h2o_slot;
+    a.tau_clamp = s->tau_clamp;
+    a.coef = s->d_coef;
+    a.planck_c = s->d_planck_c;
+    a.planck_k = s->d_planck_k;
+    a.exp_tab = s->d_exp_tab;
+    a.Tlayer = s->d_T + o * NLAY;
+    a.Tsurf = s->d_Ts + o;
+    a.vmr = s->d_vmr + o * s->nactive * NLAY;
+    a.rel_hum = s->d_rh + o * NLAY;
+    a.Tprev = s->d_Tprev + o * NLAY;
+    a.time_h = s->d_time + o;
+    a.E_down = s->d_Ed + o * NLEV;
+    a.E_up = s->d_Eu + o * NLEV;
+    a.dE = s->d_dE + o * NLAY;
+    a.dt = s->d_dt + o;
+    a.diag = s->d_diag + o * 4;
+    a.solar_col = s->has_col_solar ? s->d_solar_col + o : nullptr;
+    a.cloud_col = s->has_col_cloud ? s->d_cloud_col + o : nullptr;
+    a.tile = s->d_tile + t0 * rcm_split_tile_bytes();
+    a.part = s->d_spart + t0 * g.nsplit * rcm_split_part_doubles();
+    a.dTstat = s->d_dTstat + o;
+    a.counter = s->d_counter + which;
+    a.quota = 1 << 30;
+    return a;
+}
+
+int split_grid(const rcm_solver* s, const SplitArgs& a, int nsm) {
+    (void)s;
+    if (a.quota < a.nunits) return (a.nunits + a.quota - 1) / a.quota;  // CTAs that leave after `quota` units
+    int per_sm = 3;
+    if (const char* e = std::getenv("RCM_CTAS_PER_SM")) {  // occupancy experiments
+        const int v = std::atoi(e);
+        if (v >= 1 && v < per_sm) per_sm = v;
+    }
+    return std::min(a.nunits, nsm * per_sm);
+}
+
+// K1-K4 of one step for the columns of `a` on stream st, timed with CUDA events when `timed`
+int split_rt(rcm_solver* s, const SplitArgs& a, int nsm, cudaStream_t st, bool timed) {
+    std::pair<cudaEvent_t, cudaEvent_t> ev{};
+    if (timed) {
+        if (!s->ev_free.empty()) {
+            ev = s->ev_free.back();
+            s->ev_free.pop_back();
+        } else {
+            CU(cudaEventCreate(&ev.first));
+            CU(cudaEventCreate(&ev.second));
+        }
+        CU(cudaEventRecord(ev.first, st));
+    }
+    CU(rcm_launch_split_rt(a, split_grid(s, a, nsm), st));
+    s->launches += 1;
+    if (timed) {
+        CU(cudaEventRecord(ev.second, st));
+        s->ev_used.push_back(ev);
+        if (s->ev_used.size() >= 1024) {
+            const int rc = rcm_kernel_time_ms(s, 0, nullptr, nullptr);
+            if (rc != RCM_OK) return rc;
+        }
+    }
+    return RCM_OK;
+}
+
+// nsteps iterations of main.cpp:531-583: prep, then per step the unit kernel and one K5 kernel that finishes the step
+// and prepares the next one.
+int split_advance(rcm_solver* s, int nsteps) {
+    int st = refresh_const(s);
+    if (st != RCM_OK) return st;
+    st = ensure_split(s);
+    if (st != RCM_OK) return st;
+    const int nsm = nsm_of(s);
+    const SplitArgs a = split_args(s, 0, s->ncol, 0);
+    SplitColFlags f{};
+    f.prep = 1;
+    f.first = (s->step_index == 0);
+    f.write_all_vmr = !s->tile_vmr_valid;
+    CU(rcm_launch_split_col(a, f, s->stream));
+    s->launches += 1;
+    s->tile_vmr_valid = true;
+    for (int k = 0; k < nsteps; ++k) {
+        st = split_rt(s, a, nsm, s->stream, k < 4);  // long blocks: the first steps are timed, the rest run without event records
+        if (st != RCM_OK) return st;
+        SplitColFlags e{};
+        e.finish = 1;
+        e.prep = (k + 1 < nsteps);
+        e.first = 0;
+        e.write_out = (k + 1 == nsteps);
+        e.diag_step = k;
+        CU(rcm_launch_split_col(a, e, s->stream));
+        s->launches += 1;
+    }
+    return RCM_OK;
+}
+
 int launch(rcm_solver* s, int mode, int nsteps, bool want_diag) {
     int st = refresh_const(s);
     if (st != RCM_OK) return st;
@@ -458,6 +617,86 @@ int launch(rcm_solver* s, int mode, int nsteps, bool want_diag) {
         st = rcm_kernel_time_ms(s, 0, nullptr, nullptr);
         if (st != RCM_OK) return st;
     }
+    return RCM_OK;
+}
+
+
+// rcm_step_host on the split path: the columns travel in chunks of whole tiles through three stages on their own streams,
+//   up   (high priority): H2D of the chunk's T / Tsurf / VMRs, K5 prep
+//   rt   (two streams, alternating): the unit kernel of the chunk - its CTAs leave after four units, so the slots they
+//        hold recycle every ~0.3 ms and the small K5 kernels of the other stages get in without waiting for a whole chunk,
+//        and the next chunk's CTAs fill the SMs while this chunk's last units finish (no tail per chunk)
+//   down (high priority): K5 finish, D2H of the chunk's results
+// Results are bit-identical to rcm_update_columns + rcm_advance + rcm_get_state.
+int step_host_split(rcm_solver* s, int nchunk, const double* Tlayer_in, const double* Tsurf_in, const double* vmr_active_in,
+                    double* E_down, double* E_up, double* dE, double* Tlayer_out, double* Tsurf_out) {
+    int st = ensure_split(s);
+    if (st != RCM_OK) return st;
+    if (!s->sp_up) {
+        int lo = 0, hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // hi = greatest priority (numerically lowest)
+        CU(cudaStreamCreateWithPriority(&s->sp_up, cudaStreamNonBlocking, hi));
+        CU(cudaStreamCreateWithPriority(&s->sp_down, cudaStreamNonBlocking, hi));
+        for (int i = 0; i < 2; ++i) CU(cudaStreamCreateWithPriority(&s->sp_rt[i], cudaStreamNonBlocking, lo));
+        for (int i = 0; i < 8; ++i) {
+            CU(cudaEventCreateWithFlags(&s->sp_prep[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&s->sp_rtdone[i], cudaEventDisableTiming));
+        }
+        CU(cudaEventCreateWithFlags(&s->sp_end, cudaEventDisableTiming));
+    }
+    const int nsm = nsm_of(s);
+    const int per = ((s->ncol + nchunk - 1) / nchunk + 15) / 16 * 16;
+    CU(cudaEventRecord(s->sp_end, s->stream));  // everything queued on the solver's stream so far comes first
+    for (cudaStream_t q : {s->sp_up, s->sp_rt[0], s->sp_rt[1], s->sp_down}) CU(cudaStreamWaitEvent(q, s->sp_end, 0));
+    const size_t D = sizeof(double);
+    const int na = s->nactive;
+    int k = 0;
+    for (int c0 = 0; c0 < s->ncol; ++k, c0 += per) {
+        const int n = std::min(per, s->ncol - c0);
+        const size_t o = (size_t)c0;
+        cudaStream_t q = s->sp_up;
+        if (Tlayer_in) CU(cudaMemcpyAsync(s->d_T + o * NLAY, Tlayer_in + o * NLAY, n * NLAY * D, cudaMemcpyHostToDevice, q));
+        if (Tsurf_in) CU(cudaMemcpyAsync(s->d_Ts + o, Tsurf_in + o, n * D, cudaMemcpyHostToDevice, q));
+        if (vmr_active_in)
+            CU(cudaMemcpyAsync(s->d_vmr + o * na * NLAY, vmr_active_in + o * na * NLAY, (size_t)n * na * NLAY * D,
+                               cudaMemcpyHostToDevice, q));
+        SplitArgs a = split_args(s, c0, n, 1 + k % 2);
+        a.quota = 4;
+        SplitArgs ac = a;
+        ac.counter = nullptr;  // the K5 kernels run on other streams than the unit kernel: the counter is reset on its own stream
+        SplitColFlags f{};
+        f.prep = 1;
+        f.first = (s->step_index == 0);
+        f.write_all_vmr = !s->tile_vmr_valid || vmr_active_in != nullptr;
+        CU(rcm_launch_split_col(ac, f, q));
+        CU(cudaEventRecord(s->sp_prep[k], q));
+        q = s->sp_rt[k % 2];
+        CU(cudaStreamWaitEvent(q, s->sp_prep[k], 0));
+        CU(cudaMemsetAsync(a.counter, 0, sizeof(unsigned), q));
+        st = split_rt(s, a, nsm, q, true);
+        if (st != RCM_OK) return st;
+        CU(cudaEventRecord(s->sp_rtdone[k], q));
+        q = s->sp_down;
+        CU(cudaStreamWaitEvent(q, s->sp_rtdone[k], 0));
+        SplitColFlags e{};
+        e.finish = 1;
+        e.write_out = 1;
+        CU(rcm_launch_split_col(ac, e, q));
+        s->launches += 2;
+        if (E_down) CU(cudaMemcpyAsync(E_down + o * NLEV, s->d_Ed + o * NLEV, n * NLEV * D, cudaMemcpyDeviceToHost, q));
+        if (E_up) CU(cudaMemcpyAsync(E_up + o * NLEV, s->d_Eu + o * NLEV, n * NLEV * D, cudaMemcpyDeviceToHost, q));
+        if (dE) CU(cudaMemcpyAsync(dE + o * NLAY, s->d_dE + o * NLAY, n * NLAY * D, cudaMemcpyDeviceToHost, q));
+        if (Tlayer_out) CU(cudaMemcpyAsync(Tlayer_out + o * NLAY, s->d_T + o * NLAY, n * NLAY * D, cudaMemcpyDeviceToHost, q));
+        if (Tsurf_out) CU(cudaMemcpyAsync(Tsurf_out + o, s->d_Ts + o, n * D, cudaMemcpyDeviceToHost, q));
+    }
+    CU(cudaEventRecord(s->sp_end, s->sp_down));  // the last stage of the last chunk: everything before it is done
+    CU(cudaStreamWaitEvent(s->stream, s->sp_end, 0));
+    CU(rcm_launch_reduce_diag(s->d_diag, 1, s->ncol, s->p.dT_converged, s->d_red, s->d_ticket, s->d_scalars, s->stream));
+    s->launches += 1;
+    s->step_index += 1;
+    s->tau_valid = false;
+    s->tile_vmr_valid = true;
+    CU(cudaStreamSynchronize(s->stream));
     return RCM_OK;
 }
 
@@ -517,7 +756,7 @@ int rcm_destroy(rcm_solver* s) {
     void* ptrs[] = {s->d_xsec_file, s->d_coef, s->d_species, s->d_planck_c, s->d_planck_k, s->d_exp_tab, s->d_T, s->d_Ts, s->d_vmr, s->d_rh,
                     s->d_Tprev, s->d_time, s->d_lbl_lo, s->d_lbl_hi, s->d_lbl_tau5, s->d_lbl_h2o_ref, s->d_lbl_o3_ref, s->d_sH, s->d_sO,
                     s->d_dTstat, s->d_part, s->d_Ed, s->d_Eu, s->d_dE, s->d_dt, s->d_diag, s->d_scalars, s->d_red, s->d_tau,
-                    s->d_lowpos, s->d_solar_col, s->d_cloud_col, s->d_ticket};
+                    s->d_lowpos, s->d_solar_col, s->d_cloud_col, s->d_ticket, s->d_tile, s->d_spart, s->d_counter};
     for (void* q : ptrs)
         if (q) cudaFree(q);
     for (auto& e : s->ev_free) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -527,6 +766,13 @@ int rcm_destroy(rcm_solver* s) {
         if (s->pipe_done[i]) cudaEventDestroy(s->pipe_done[i]);
     }
     if (s->pipe_start) cudaEventDestroy(s->pipe_start);
+    for (cudaStream_t q : {s->sp_up, s->sp_rt[0], s->sp_rt[1], s->sp_down})
+        if (q) cudaStreamDestroy(q);
+    for (int i = 0; i < 8; ++i) {
+        if (s->sp_prep[i]) cudaEventDestroy(s->sp_prep[i]);
+        if (s->sp_rtdone[i]) cudaEventDestroy(s->sp_rtdone[i]);
+    }
+    if (s->sp_end) cudaEventDestroy(s->sp_end);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     delete s;
     return RCM_OK;
@@ -557,6 +803,7 @@ int rcm_set_option(rcm_solver* s, int option, int value) {
     }
     if (option == 1) {
         s->opt_config = value;
+        s->tile_vmr_valid = false;
         return RCM_OK;
     }
     if (option == 2) {
@@ -570,6 +817,11 @@ int rcm_set_option(rcm_solver* s, int option, int value) {
     if (option == 4) {
         s->opt_angle_pairs = value ? 1 : 0;
         s->const_dirty = true;
+        return RCM_OK;
+    }
+    if (option == 5) {
+        s->opt_path = value ? 1 : 0;
+        s->tile_vmr_valid = false;
         return RCM_OK;
     }
     return fail(s, RCM_ERR_ARG, "unknown option");
@@ -726,6 +978,7 @@ int rcm_set_columns(rcm_solver* s, int ncol, const double* plevel_hPa, const dou
     CU(cudaStreamSynchronize(s->stream));
     s->step_index = 0;
     s->tau_valid = false;
+    s->tile_vmr_valid = false;
     s->has_col_solar = s->has_col_cloud = false;  // per-column forcing belongs to the column set it was given for
     return RCM_OK;
 }
@@ -796,6 +1049,7 @@ int rcm_update_columns(rcm_solver* s, const double* Tlayer, const double* Tsurf,
     if (Tsurf) CU(cudaMemcpyAsync(s->d_Ts, Tsurf, n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
     if (vmr_active)
         CU(cudaMemcpyAsync(s->d_vmr, vmr_active, n * s->nactive * NLAY * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    if (vmr_active) s->tile_vmr_valid = false;
     s->tau_valid = false;
     return RCM_OK;
 }
@@ -864,11 +1118,11 @@ static int lbl_advance(rcm_solver* s, int nsteps) {
     a.ncol = s->ncol;
     a.ntiles = (s->ncol + RCM_LBL_C - 1) / RCM_LBL_C;
     a.nwvl = s->lbl_nwvl;
-    // enough (tile, wavelength chunk) CTAs to fill the GPU a few times over; chunk length a multiple of 3 groups
-    int nchunks = (4 * 444 + a.ntiles - 1) / a.ntiles;
-    if (nchunks > a.nwvl / 48) nchunks = a.nwvl / 48;
-    if (nchunks < 1) nchunks = 1;
-    a.chunk_len = ((a.nwvl + nchunks - 1) / nchunks + 3) / 4 * 4;  // a multiple of the 4 wavelength groups
+    // (tile, wavelength chunk) CTAs with a FIXED chunk of 128 wavelengths (32 rounds of the 4 wavelength groups): the
+    // order of the spectral sum - registers over a chunk's rounds, groups, chunks - does not depend on how many columns
+    // this GPU owns (a shard of an ensemble is bit-identical to the same columns inside the whole), and 4,096 columns x
+    // 20,000 wavelengths are 40,192 units for the hardware scheduler to balance instead of 1,792 (4.04 rounds of 444)
+    a.chunk_len = 128;
     a.nchunks = (a.nwvl + a.chunk_len - 1) / a.chunk_len;
     const size_t need = (size_t)a.nchunks * n * 42;
     if (need > s->part_cap) {
@@ -897,7 +1151,20 @@ static int lbl_advance(rcm_solver* s, int nsteps) {
     for (int k = 0; k < nsteps; ++k) {
         a.step_index = s->step_index + k;
         a.diag = s->d_diag + (size_t)k * s->ncol * 4;
-        CU(rcm_launch_lbl_step(a, s->stream));
+        std::pair<cudaEvent_t, cudaEvent_t> ev{};
+        if (!s->ev_free.empty()) {
+            ev = s->ev_free.back();
+            s->ev_free.pop_back();
+        } else {
+            CU(cudaEventCreate(&ev.first));
+            CU(cudaEventCreate(&ev.second));
+        }
+        CU(rcm_launch_lbl_step(a, s->stream, ev.first, ev.second));
+        s->ev_used.push_back(ev);
+        if (s->ev_used.size() >= 1024) {
+            st = rcm_kernel_time_ms(s, 0, nullptr, nullptr);
+            if (st != RCM_OK) return st;
+        }
         s->launches += 3;
     }
     return RCM_OK;
@@ -918,7 +1185,7 @@ int rcm_advance_async(rcm_solver* s, int nsteps, double** d_scalars) {
         if (d_scalars) *d_scalars = s->d_scalars;
         return RCM_OK;
     }
-    st = launch(s, MODE_STEP, nsteps, true);
+    st = use_split(s) ? split_advance(s, nsteps) : launch(s, MODE_STEP, nsteps, true);
     if (st != RCM_OK) return st;
     CU(rcm_launch_reduce_diag(s->d_diag, nsteps, s->ncol, s->p.dT_converged, s->d_red, s->d_ticket, s->d_scalars, s->stream));
     s->launches += 1;
@@ -1105,6 +1372,7 @@ int rcm_load_checkpoint(rcm_solver* s, const char* path) {
     s->has_col_solar = hdr[4] != 0;
     s->has_col_cloud = hdr[5] != 0;
     s->tau_valid = false;
+    s->tile_vmr_valid = false;
     return RCM_OK;
 }
 
@@ -1136,6 +1404,8 @@ int rcm_step_host(rcm_solver* s, const double* Tlayer_in, const double* Tsurf_in
         }
         CU(cudaEventCreateWithFlags(&s->pipe_start, cudaEventDisableTiming));
     }
+    if (use_split(s))
+        return step_host_split(s, nchunk, Tlayer_in, Tsurf_in, vmr_active_in, E_down, E_up, dE, Tlayer_out, Tsurf_out);
     const int nsm = nsm_of(s);
     Part whole[2];
     plan_parts(s, s->ncol, nsm, whole);

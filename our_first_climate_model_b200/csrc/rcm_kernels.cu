@@ -173,6 +173,7 @@ __global__ void __launch_bounds__(256) rcm_microbench_kernel(double* out, long i
 }
 
 #include "rcm_lbl_kernels.cuh"
+#include "rcm_split_kernels.cuh"
 
 // ------------------------------------------------------------------------------------------
 // Solar setup per column: doubling_adding + solar_radiative_transfer_setup
@@ -272,6 +273,23 @@ cudaError_t rcm_launch_step(int mode, const StepArgs& a, int nactive, int grid, 
     return cudaErrorInvalidValue;
 }
 
+size_t rcm_split_tile_bytes() { return TILE_BYTES; }
+size_t rcm_split_part_doubles() { return SPLIT_PART; }
+int rcm_split_ipu() { return SPLIT_IPU; }
+
+cudaError_t rcm_launch_split_col(const SplitArgs& a, const SplitColFlags& f, cudaStream_t st) {
+    rcm_split_col_kernel<<<a.ntiles, SPLIT_COL_NT, 0, st>>>(a, f);
+    return cudaGetLastError();
+}
+
+cudaError_t rcm_launch_split_rt(const SplitArgs& a, int grid, cudaStream_t st) {
+    auto kern = a.clampk ? rcm_split_rt_kernel<true> : rcm_split_rt_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPLIT_SMEM);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, SPLIT_NT, SPLIT_SMEM, st>>>(a);
+    return cudaGetLastError();
+}
+
 size_t rcm_reduce_scratch_doubles(int nsteps) { return (size_t)nsteps * RED_BLOCKS * 4; }
 
 // scratch: rcm_reduce_scratch_doubles(capacity) doubles; ticket: one counter per step of the CAPACITY the buffers were
@@ -318,14 +336,16 @@ size_t rcm_lbl_smem_bytes(int C, int nthreads) {
             (size_t)NLEV * (nthreads / 2)) * sizeof(double);
 }
 
-cudaError_t rcm_launch_lbl_step(const LblArgs& a, cudaStream_t st) {
+cudaError_t rcm_launch_lbl_step(const LblArgs& a, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1) {
     constexpr int C = RCM_LBL_C, NT = RCM_LBL_NT;
     rcm_lbl_prep_kernel<<<(a.ncol + 127) / 128, 128, 0, st>>>(a);
     const size_t smem = rcm_lbl_smem_bytes(C, NT);
     auto kern = a.clampk ? rcm_lbl_rt_kernel<C, NT, true> : rcm_lbl_rt_kernel<C, NT, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    if (ev0) cudaEventRecord(ev0, st);
     kern<<<a.ntiles * a.nchunks, NT, smem, st>>>(a);
+    if (ev1) cudaEventRecord(ev1, st);
     rcm_lbl_finish_kernel<<<(a.ncol + 127) / 128, 128, 0, st>>>(a);
     return cudaGetLastError();
 }

@@ -120,6 +120,40 @@ struct LblArgs {
     const double* solar_col; const double* cloud_col;  // as StepArgs
 };
 
+// Split path (rcm_split_kernels.cuh): the repwvl step as a per-tile K5 kernel and a (tile, wavelength split) K1-K4 kernel.
+struct SplitArgs {
+    int ncol;            // columns in this launch (pointers below are offset to its first column / tile)
+    int diag_ncol;       // columns of the whole ensemble = row length of diag
+    int ntiles, nsplit, ipu, nitem, nunits;  // tiles of 16 columns; splits per tile; wavelength rounds per split / per tile
+    int stage_rows, clampk, h2o_slot;
+    double tau_clamp;
+    const double* __restrict__ coef;
+    const double* __restrict__ planck_c;
+    const double* __restrict__ planck_k;
+    const double* __restrict__ exp_tab;
+    double* Tlayer; double* Tsurf; double* vmr; const double* rel_hum; double* Tprev; float* time_h;
+    double* E_down; double* E_up; double* dE; double* dt; double* diag;
+    const double* solar_col; const double* cloud_col;
+    unsigned char* tile;  // [ntiles][TILE_BYTES] everything the unit kernel needs for a tile, written by the K5 kernel
+    double* part;         // [ntiles][nsplit][42][16] partial fluxes of the units
+    double* dTstat;       // [ncol] stationarity diagnostic of the step being computed
+    unsigned* counter;    // work counter of the unit kernel (reset by the K5 kernel in front of it; NULL there: leave it alone)
+    int quota;            // units a CTA of the unit kernel takes before it exits (persistent: a huge number)
+};
+struct SplitColFlags {
+    int finish;         // sum the partial fluxes of a step, dE, time step, T update
+    int prep;           // then prepare the next step (sort, feedback, indices, tile block)
+    int first;          // the step being prepared is iteration 0: tau from the initial, unsorted profile (main.cpp:500-504)
+    int write_all_vmr;  // (re)write every species into the tile block, not just H2O
+    int write_out;      // store E_down, E_up, dE, dt of the finished step
+    int diag_step;      // row of diag the finished step writes
+};
+size_t rcm_split_tile_bytes();
+size_t rcm_split_part_doubles();
+int rcm_split_ipu();
+cudaError_t rcm_launch_split_col(const SplitArgs& a, const SplitColFlags& f, cudaStream_t st);
+cudaError_t rcm_launch_split_rt(const SplitArgs& a, int grid, cudaStream_t st);
+
 enum { MODE_STEP = 0, MODE_TAU = 1, MODE_RT = 2 };
 
 size_t rcm_step_smem_bytes(int C, int nactive, int nthreads);
@@ -133,7 +167,8 @@ cudaError_t rcm_launch_coef(const double* xsec_file, double* coef, int nt, int n
 cudaError_t rcm_launch_microbench(int which, double* out, const double* tab, long iters, int grid,
                                   cudaStream_t st);
 size_t rcm_lbl_smem_bytes(int C, int nthreads);
-cudaError_t rcm_launch_lbl_step(const LblArgs& a, cudaStream_t st);
+// ev0 / ev1 (may be NULL): recorded around the radiative-transfer kernel, the dominant one of the three
+cudaError_t rcm_launch_lbl_step(const LblArgs& a, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1);
 // doubling_adding + solar_radiative_transfer_setup (main.cpp:214-264) for n columns, one thread each.  tau_s / mu_s /
 // albedo: per-column arrays or NULL (then the scalar in sp).  Outputs (any may be NULL): solar_irr, r_total, and
 // cloud_tau = tau_s / 2 (the thermal grey-cloud term of the same cloud, main.cpp:267).

@@ -72,7 +72,7 @@ def test_radiative_transfer_given_tau(solver, rcm, golden, n, cubes):
     # heating rates are differences of fluxes: tolerance relative to the column's flux scale
     scale = np.max(np.abs(golden[f"s1_E_up_{n}"]), axis=-1, keepdims=True)
     assert relerr(dE, golden[f"s1_dE_{n}"], scale) < RTOL
-    assert relerr(dE, golden[f"s1_dE_{n}"]) < 1e-9  # and relative to max|dE| of the column
+    assert relerr(dE, golden[f"s1_dE_{n}"]) < RTOL  # and relative to max|dE| of the column
 
 
 @pytest.mark.parametrize("nw", [7, 150])
@@ -127,13 +127,14 @@ def test_one_fused_step(solver, rcm, golden, n):
     assert relerr(st["E_up"], golden[f"s1_E_up_{n}"]) < RTOL
     scale = np.max(np.abs(golden[f"s1_E_up_{n}"]), axis=-1, keepdims=True)
     assert relerr(st["dE"], golden[f"s1_dE_{n}"], scale) < RTOL
-    np.testing.assert_allclose(st["dt"], golden[f"s1_dt_{n}"], rtol=1e-9)
+    assert relerr(st["dE"], golden[f"s1_dE_{n}"]) < RTOL  # heating rates: 1e-10 also relative to the column's own max|dE|
+    np.testing.assert_allclose(st["dt"], golden[f"s1_dt_{n}"], rtol=1e-10)
     np.testing.assert_allclose(st["Tlayer"], golden[f"s1_Tlayer_{n}"], rtol=1e-11)
     np.testing.assert_allclose(st["Tsurf"], golden[f"s1_Tsurf_{n}"], rtol=1e-11)
     np.testing.assert_allclose(st["time_h"], golden[f"s1_time_h_{n}"], rtol=1e-6)
     toa = golden["solar_irr"] - golden[f"s1_E_up_{n}"][:, 0]
     np.testing.assert_allclose(sc[0, 0], toa.sum(), rtol=1e-10)
-    np.testing.assert_allclose(sc[0, 3], np.abs(golden[f"s1_dE_{n}"]).max(), rtol=1e-9)
+    np.testing.assert_allclose(sc[0, 3], np.abs(golden[f"s1_dE_{n}"]).max(), rtol=1e-10)
 
 
 @pytest.mark.parametrize("n", [20, 100])
@@ -344,12 +345,11 @@ def test_two_million_columns_index_arithmetic(rcm, golden):
     ncol = base * rep
     s = rcm.Solver(0)
     s.set_repwvl_table_from(rcm.Table(table_path(10)))
-    s.set_option(1, 1)  # the 16-column tile shape of big ensembles also for the 16-column run: same order of additions
+    # (the split path's order of additions does not depend on the ensemble size: no tile shape to force)
     s.set_columns(golden["plevel"], golden["Tlayer"], golden["Tsurf"], golden["vmr9"], golden["rel_hum"])
     s.advance(2)
     small = s.get_state()
     tau_small, _, lt_small = s.build_tau()
-    s.set_option(1, 0)
     tile = lambda a: np.tile(a, (rep,) + (1,) * (a.ndim - 1))
     vmr9 = tile(golden["vmr9"])
     s.set_columns(golden["plevel"], tile(golden["Tlayer"]), tile(golden["Tsurf"]), vmr9, tile(golden["rel_hum"]))
