@@ -367,7 +367,7 @@ def run_b200(args, rank, world, local_rank):
     # ---- strong scaling (BASELINE configs[3] as north_star states it): ONE 65,536-column ensemble over the ranks ----
     strong = None
     total = args.strong_total
-    if world > 1:
+    if not args.no_strong:
         import hashlib
         lo, hi = rdist.shard_range(total, rank, world)
         sl = slice(lo, hi)
@@ -400,6 +400,8 @@ def run_b200(args, rank, world, local_rank):
                   "kernel_ms_per_rank": {"min": min(ks_ranks), "max": max(ks_ranks)},
                   "driver_blocks": {"steps_per_block": blk, "ms_per_step": ms_b / (2 * blk),
                                     "value": total * nwvl * NLAY * 2 * blk / (ms_b * 1e-3)},
+                  # Tlayer of the ensemble's first 64 columns after check_steps iterations: the same bytes for every N
+                  # (per-column results do not depend on the sharding - split path)
                   "check_T_sha_first64": chk, "check_steps": args.warmup + args.steps + 3 * blk}
     lbl = None
     if not args.no_lbl:
@@ -408,9 +410,6 @@ def run_b200(args, rank, world, local_rank):
 
     if rank != 0:
         return 0
-    if world == 1:
-        strong = {"columns_total": ncol, "columns_per_gpu": ncol, "value": value, "unit": UNIT,
-                  "ms_per_step": ms_total / args.steps, "scaling": "strong", "note": "one GPU: the weak and the strong job coincide"}
     # ---- roofline of the dominant kernel: FP64 pipe -------------------------------------------------------
     cap = load_capture()
     exec_per_unit = cap["step"]["exec_fp64_per_unit"]
@@ -640,6 +639,7 @@ def main():
     ap.add_argument("--lbl-cpu-cols", type=int, default=8)
     ap.add_argument("--no-lbl", action="store_true", help="skip the LBL block of the default line")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the timed run")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling block (one ensemble over the ranks)")
     ap.add_argument("--strong-total", type=int, default=65536, help="columns of the strong-scaling ensemble (N > 1)")
     ap.add_argument("--ring", type=int, default=32, help="slots of the asynchronous scalar exchange")
     args = ap.parse_args()

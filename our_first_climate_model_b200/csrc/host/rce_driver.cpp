@@ -9,6 +9,13 @@
 //   rcm_rce --atm test.atm --table Reduced100Forcing.nc [--ncol N] [--seed S] [--max-steps M] [--check-every K]
 //           [--dT 1e-3] [--device D] [--out output.txt] [--checkpoint file] [--resume file] [--steps-exact]
 //   rcm_rce --atm fpda.lbl.atm --lbl DIR [--co2-factor F] ...     line-by-line: DIR/lbl.{h2o,co2,o3,ch4,n2o}.asc
+//   rcm_rce ... --gpus N                                          the same ensemble sharded over N GPUs of this node
+//
+// --gpus N (N > 1): one process, one host thread and one solver per GPU, contiguous blocks of columns per GPU (tables
+// replicated), NCCL directly: after every block of --check-every fused iterations ONE pair of ncclAllReduce calls (sum,
+// max) over the block's four scalars per step decides - identically on every GPU - whether the whole ensemble is
+// stationary.  Nothing else crosses GPUs.  Per-column results do not depend on N (the solver's order of additions is
+// fixed per column): the profile rows of an N-GPU run are byte-identical to the 1-GPU run's.
 //
 // The line-by-line form reads the five tables with the drop-in of ASCII_file2xy2D (lbl.arts/testlblarts.cpp:24-26 is the
 // reference's only call of that reader); a six-column .atm (lbl.arts/README:1-3) gets the well-mixed CO2 / CH4 / N2O of
@@ -16,11 +23,16 @@
 //
 // --steps-exact runs exactly max_steps iterations (the reference's n_steps semantics, main.cpp:83) instead of
 // stopping at stationarity.  Exit code 0, or 1 with the library's error text on stderr.  No CPU fallback.
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
+
+#include <cuda_runtime_api.h>
+#include <nccl.h>
 
 #include "rcm_b200.h"
 
@@ -31,12 +43,94 @@ int die(const char* what, int st, const rcm_solver* s) {
     return 1;
 }
 
+// ---- N GPUs: one thread per GPU, columns [lo, hi) each ---------------------------------------------------------
+struct Shard {
+    int dev = 0, lo = 0, hi = 0;
+    rcm_solver* s = nullptr;
+    cudaStream_t stream = nullptr;
+    ncclComm_t comm = nullptr;
+    double *d_sum = nullptr, *d_max = nullptr;  // [check_every][4] reduced scalars of a block
+    long done = 0;
+    rcm_step_scalars last{};
+    std::string err;
+};
+
+struct Job {  // what every shard needs; host arrays cover the WHOLE ensemble
+    const rcm_params* p;
+    const rcm_table* table;  // repwvl, or NULL
+    const std::vector<double>*wvl, *tau5;
+    int lbl_nwvl;
+    double co2_factor;
+    const double *plevel, *Tlayer, *Tsurf, *vmr9, *rel_hum;
+    int ncol;
+    long max_steps;
+    int check_every, steps_exact;
+    std::string resume, ckpt;
+    double *T_out, *Ts_out, *Eu_out;
+    float* time_out;
+};
+
+std::atomic<int> g_failed{0};
+
+void run_shard(Shard* sh, const Job* j) {
+    auto fail = [&](const char* what, int st) {
+        sh->err = std::string(what) + ": " + rcm_status_string(st) + (sh->s ? std::string(" - ") + rcm_last_error(sh->s) : "");
+        g_failed.store(1);
+    };
+    constexpr int NLAY = RCM_NLAYER, NLEV = RCM_NLEVEL;
+    const size_t lo = (size_t)sh->lo, n = (size_t)(sh->hi - sh->lo);
+    int st = rcm_create(sh->dev, j->p, &sh->s);
+    if (st != RCM_OK) return fail("rcm_create", st);
+    if (cudaSetDevice(sh->dev) != cudaSuccess || cudaStreamCreateWithFlags(&sh->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc((void**)&sh->d_sum, (size_t)j->check_every * 4 * sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void**)&sh->d_max, (size_t)j->check_every * 4 * sizeof(double)) != cudaSuccess)
+        return fail("cuda setup", RCM_ERR_CUDA);
+    rcm_set_stream(sh->s, sh->stream);  // the solver's kernels and the NCCL calls share one stream: ordered without events
+    st = j->table ? rcm_set_repwvl_table_from(sh->s, j->table)
+                  : rcm_set_lbl_tables(sh->s, j->wvl->data(), j->tau5->data(), j->lbl_nwvl, j->vmr9 + 0 * NLAY, j->vmr9 + 2 * NLAY,
+                                       j->co2_factor);
+    if (st != RCM_OK) return fail("tables", st);
+    if (!j->resume.empty()) {
+        st = rcm_load_checkpoint(sh->s, (j->resume + ".gpu" + std::to_string(sh->dev)).c_str());
+        if (st == RCM_OK && rcm_column_count(sh->s) != (int)n) st = RCM_ERR_STATE;
+    } else {
+        st = rcm_set_columns(sh->s, (int)n, j->plevel, j->Tlayer + lo * NLAY, j->Tsurf + lo, j->vmr9 + lo * RCM_NSPECIES * NLAY,
+                             j->rel_hum + lo * NLAY);
+    }
+    if (st != RCM_OK) return fail("columns", st);
+    // ---- the time loop (main.cpp:531-583) in blocks; one allreduce pair per block ------------------------------
+    std::vector<double> hs(4), hm(4);
+    while (sh->done < j->max_steps && !g_failed.load()) {
+        const int k = (int)((j->max_steps - sh->done < j->check_every) ? (j->max_steps - sh->done) : j->check_every);
+        double* d_sc = nullptr;
+        st = rcm_advance_async(sh->s, k, &d_sc);
+        if (st != RCM_OK) return fail("rcm_advance_async", st);
+        if (ncclAllReduce(d_sc, sh->d_sum, (size_t)k * 4, ncclDouble, ncclSum, sh->comm, sh->stream) != ncclSuccess ||
+            ncclAllReduce(d_sc, sh->d_max, (size_t)k * 4, ncclDouble, ncclMax, sh->comm, sh->stream) != ncclSuccess)
+            return fail("ncclAllReduce", RCM_ERR_CUDA);
+        cudaMemcpyAsync(hs.data(), sh->d_sum + (size_t)(k - 1) * 4, 4 * sizeof(double), cudaMemcpyDeviceToHost, sh->stream);
+        cudaMemcpyAsync(hm.data(), sh->d_max + (size_t)(k - 1) * 4, 4 * sizeof(double), cudaMemcpyDeviceToHost, sh->stream);
+        if (cudaStreamSynchronize(sh->stream) != cudaSuccess) return fail("block", RCM_ERR_CUDA);
+        sh->done += k;
+        sh->last = {hs[0], hm[1], hs[2], hm[3]};  // sums: TOA net, converged count; maxima: dT, |dE|
+        if (!j->steps_exact && sh->last.n_converged >= (double)j->ncol) break;  // the same numbers on every GPU
+    }
+    if (g_failed.load()) return;
+    st = rcm_get_state(sh->s, j->T_out + lo * NLAY, j->Ts_out + lo, nullptr, j->time_out + lo, nullptr, j->Eu_out + lo * NLEV, nullptr,
+                       nullptr);
+    if (st != RCM_OK) return fail("rcm_get_state", st);
+    if (!j->ckpt.empty()) {
+        st = rcm_save_checkpoint(sh->s, (j->ckpt + ".gpu" + std::to_string(sh->dev)).c_str());
+        if (st != RCM_OK) return fail("rcm_save_checkpoint", st);
+    }
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
     std::string atm_path, table_path, lbl_dir, out_path = "output.txt", ckpt_path, resume_path;
     double co2_factor = 1.0;
-    int ncol = 1, device = 0, check_every = 250, steps_exact = 0;
+    int ncol = 1, device = 0, check_every = 250, steps_exact = 0, gpus = 1;
     long max_steps = 6000;
     unsigned long long seed = 12345;
     double dT = 1e-3;
@@ -57,14 +151,16 @@ int main(int argc, char** argv) {
         else if (a == "--checkpoint") ckpt_path = val();
         else if (a == "--resume") resume_path = val();
         else if (a == "--steps-exact") steps_exact = 1;
+        else if (a == "--gpus") gpus = std::atoi(val());
         else {
             std::fprintf(stderr, "rcm_rce: unknown argument %s\n", a.c_str());
             return 1;
         }
     }
-    if (atm_path.empty() || (table_path.empty() == lbl_dir.empty()) || ncol < 1 || max_steps < 1 || check_every < 1) {
+    if (atm_path.empty() || (table_path.empty() == lbl_dir.empty()) || ncol < 1 || max_steps < 1 || check_every < 1 || gpus < 1 ||
+        gpus > ncol) {
         std::fprintf(stderr, "usage: rcm_rce --atm FILE (--table FILE | --lbl DIR [--co2-factor F]) [--ncol N] [--seed S] [--max-steps M] [--check-every K] "
-                             "[--dT K/step] [--device D] [--out FILE] [--checkpoint FILE] [--resume FILE] [--steps-exact]\n");
+                             "[--dT K/step] [--device D] [--out FILE] [--checkpoint FILE] [--resume FILE] [--steps-exact] [--gpus N]\n");
         return 1;
     }
 
@@ -107,6 +203,84 @@ int main(int argc, char** argv) {
     rcm_solar_setup(&sp, sol);
     p.solar_irr = sol[6];
     p.dT_converged = dT;
+    if (gpus > 1) {
+        // ---- one thread and one solver per GPU, NCCL for the block scalars --------------------------------------
+        if (rcm_device_count() < gpus) {
+            std::fprintf(stderr, "rcm_rce: --gpus %d but %d CUDA device(s) visible\n", gpus, rcm_device_count());
+            return 1;
+        }
+        rcm_table* table = nullptr;
+        std::vector<double> wvl, tau5;
+        int nwvl = 0;
+        if (lbl) {
+            const char* names[5] = {"h2o", "co2", "o3", "ch4", "n2o"};
+            for (int k = 0; k < 5; ++k) {
+                const std::string path = lbl_dir + "/lbl." + names[k] + ".asc";
+                int nx = 0, ny = 0;
+                double *x = nullptr, *y = nullptr;
+                const int rc = rcm_ascii_file2xy2D(path.c_str(), &nx, &ny, &x, &y);
+                if (rc != 0 || ny != NLAY || nx < 2 || (k > 0 && (nx != nwvl || std::memcmp(wvl.data(), x, (size_t)nx * sizeof(double)) != 0))) {
+                    std::fprintf(stderr, "rcm_rce: %s: reader status %d, %d wavelengths x %d layers\n", path.c_str(), rc, nx, ny);
+                    return 1;
+                }
+                if (k == 0) {
+                    nwvl = nx;
+                    wvl.assign(x, x + nx);
+                    tau5.resize((size_t)5 * nx * NLAY);
+                }
+                std::memcpy(&tau5[(size_t)k * nx * NLAY], y, (size_t)nx * NLAY * sizeof(double));
+                rcm_free(x);
+                rcm_free(y);
+            }
+        } else {
+            st = rcm_table_load(table_path.c_str(), &table);
+            if (st != RCM_OK) return die(table_path.c_str(), st, nullptr);
+        }
+        std::vector<double> T(n * NLAY), Ts(n), Eu(n * NLEV);
+        std::vector<float> time_h(n);
+        Job job{&p, table, &wvl, &tau5, nwvl, co2_factor, plevel, Tlayer.data(), Tsurf.data(), vmr9.data(), rel_hum.data(), ncol,
+                max_steps, check_every, steps_exact, resume_path, ckpt_path, T.data(), Ts.data(), Eu.data(), time_h.data()};
+        std::vector<Shard> shards((size_t)gpus);
+        std::vector<ncclComm_t> comms((size_t)gpus);
+        std::vector<int> devs((size_t)gpus);
+        for (int d = 0; d < gpus; ++d) devs[d] = d;
+        if (ncclCommInitAll(comms.data(), gpus, devs.data()) != ncclSuccess) {
+            std::fprintf(stderr, "rcm_rce: ncclCommInitAll failed for %d GPUs\n", gpus);
+            return 1;
+        }
+        const int base = ncol / gpus, rem = ncol % gpus;  // contiguous blocks, sizes differ by at most one
+        for (int d = 0, lo = 0; d < gpus; ++d) {
+            shards[d].dev = d;
+            shards[d].lo = lo;
+            shards[d].hi = lo += base + (d < rem ? 1 : 0);
+            shards[d].comm = comms[d];
+        }
+        std::vector<std::thread> th;
+        for (int d = 0; d < gpus; ++d) th.emplace_back(run_shard, &shards[d], &job);
+        for (auto& t : th) t.join();
+        int bad = 0;
+        for (auto& sh : shards)
+            if (!sh.err.empty()) {
+                std::fprintf(stderr, "rcm_rce: GPU %d: %s\n", sh.dev, sh.err.c_str());
+                bad = 1;
+            }
+        for (auto& sh : shards) {
+            if (sh.s) rcm_destroy(sh.s);
+            if (sh.comm) ncclCommDestroy(sh.comm);
+        }
+        if (table) rcm_table_free(table);
+        if (bad) return 1;
+        st = rcm_write_profiles(out_path.c_str(), 0, 1, ncol, plevel, T.data(), time_h.data(), ncol > 1);
+        if (st != RCM_OK) return die(out_path.c_str(), st, nullptr);
+        const rcm_step_scalars& last = shards[0].last;
+        double ts_mean = 0.0;
+        for (size_t c = 0; c < n; ++c) ts_mean += Ts[c];
+        std::printf("rcm_rce: %d columns on %d GPUs, %ld iterations, %d/%d stationary (< %g K per step), max dT %.3e K, mean TOA net %.4f W/m2, "
+                    "mean T_surface %.4f K, member 0: T_surface %.6f K, OLR %.6f W/m2, time %.2f h\n",
+                    ncol, gpus, shards[0].done, (int)last.n_converged, ncol, dT, last.max_dT, last.toa_net_sum / ncol, ts_mean / ncol,
+                    Ts[0], Eu[0], (double)time_h[0]);
+        return 0;
+    }
     rcm_solver* s = nullptr;
     st = rcm_create(device, &p, &s);
     if (st != RCM_OK) return die("rcm_create", st, nullptr);

@@ -29,6 +29,12 @@ def golden_misc():
     return np.load(os.path.join(GOLDEN, "ref_misc.npz"))
 
 
+@pytest.fixture(scope="session")
+def golden_eq():
+    """16 columns x 6,000 reference iterations (tools/make_golden_equilibrium.py)."""
+    return np.load(os.path.join(GOLDEN, "ref_equilibrium.npz"))
+
+
 def table_path(n):
     return os.path.join(GOLDEN, f"Reduced{n}Forcing.rcmtab")
 

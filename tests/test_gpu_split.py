@@ -127,3 +127,25 @@ def test_step_host_pipeline_on_the_split_path(rcm):
     for k in ("E_down", "E_up", "dE", "Tlayer", "Tsurf"):
         assert np.array_equal(a1[k], b1[k]) and np.array_equal(a2[k], b2[k]), k
     s.close()
+
+
+def test_perturbed_members_reach_the_reference_equilibrium(rcm, golden, golden_eq):
+    """north_star: "the equilibrium temperature profile within 1e-3 K" - for PERTURBED ensemble members (13 of the 16
+    columns; two more sit exactly on table nodes), 6,000 iterations of main.cpp:531-583 by the unmodified reference
+    (tests/golden/ref_equilibrium.npz) against the GPU run in blocks of 250 fused steps."""
+    s = rcm.Solver(0)
+    s.set_repwvl_table_from(rcm.Table(table_path(100)))
+    s.set_columns(golden["plevel"], golden["Tlayer"], golden["Tsurf"], golden["vmr9"], golden["rel_hum"])
+    n = int(golden_eq["nsteps"])
+    sc = None
+    for _ in range(n // 250):
+        sc = s.advance(250)
+    st = s.get_state()
+    s.close()
+    dT = np.abs(st["Tlayer"] - golden_eq["Tlayer"]).max(axis=1)
+    assert dT.max() < 1e-3, dT
+    assert np.abs(st["Tsurf"] - golden_eq["Tsurf"]).max() < 1e-3
+    # far tighter in practice: the trajectory is stable (SURVEY section 0, fact 12)
+    assert dT.max() < 1e-6 and relerr(st["E_up"], golden_eq["E_up"]) < 1e-9
+    np.testing.assert_allclose(st["h2o"], golden_eq["h2o"], rtol=1e-8)
+    assert sc[-1, 1] < 1e-2 and golden_eq["Tsurf"].max() - golden_eq["Tsurf"].min() > 10.0  # members really differ

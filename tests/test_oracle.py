@@ -143,3 +143,52 @@ def test_lbl_composition_uses_reference_components(port):
     assert np.all(hi > lo) and np.allclose(hi[:-1], lo[1:])
     assert np.array_equal(np.array([R.cplkavg(a, b, 250.0) for a, b in zip(lo, hi)]),
                           np.array([port.cplkavg(a, b, 250.0)[0] for a, b in zip(lo, hi)]))
+
+
+@needs_ref
+def test_lbl_step_sweeps_equal_the_reference_radiative_transfer_by_linearity(port, golden):
+    """Path-level pin of the LBL composition's sweep / accumulation structure to the REFERENCE's radiative_transfer
+    (main.cpp:320-344).  Fluxes are linear in the sources (B_0 .. B_19, B_surface) for a given tau.  The reference ties its
+    source to T through the monochromatic Planck function times a spectral weight, so one source at a time is handed to
+    it: layer l at its temperature with weights w_i = cplkavg(lo_i, hi_i, T_l) / planck(lambda_i, 1, T_l) - then the
+    reference's w_i * planck(lambda_i, T_l) IS the band-integrated source of the LBL step - and every other layer and the
+    surface at 1 K (their Planck source is exactly 0).  The 21 reference runs add up to the LBL port's step."""
+    rng = np.random.default_rng(5)
+    nw = 24
+    wvl = np.sort(10 ** rng.uniform(3.7, 4.9, nw))
+    lo, hi = port.lbl_bin_edges(wvl)
+    pl, conv = golden["plevel"], golden["conv"]
+    T0 = golden["Tlayer"][3] + rng.uniform(-2, 2, 20)
+    Ts = 291.3
+    Tsorted = -np.sort(-(T0 * conv)) / conv                      # main.cpp:536-540, as the step does first
+    tau = 10 ** rng.uniform(-4, 1.3, (nw, 20))
+    tau5 = np.zeros((5, nw, 20))
+    tau5[3] = tau                                                # the unscaled CH4 slot carries the whole optical depth
+    h2o_ref = golden["vmr9"][3, 0]
+    got = port.lbl_advance(wvl, tau5, pl, golden["rel_hum"][3:4], h2o_ref, np.ones((1, 20)), 1.0, 0.0, T0[None], Ts,
+                           h2o_ref[None], 1, cloud_on=False)
+    L = port.lib()
+    Ed, Eu = np.zeros(21), np.zeros(21)
+    for src in range(21):
+        Tsrc = Ts if src == 20 else Tsorted[src]
+        w = np.array([R.cplkavg(a, b, Tsrc) / L.rcmo_planck(float(x), 1.0, float(Tsrc)) for a, b, x in zip(lo, hi, wvl)])
+        Tl = np.full(20, 1.0)
+        if src < 20:
+            Tl[src] = Tsrc
+        ed, eu, _ = R.radiative_transfer(tau, wvl, w, Tl, Ts if src == 20 else 1.0, 0.0)
+        Ed += ed
+        Eu += eu
+    scale = np.abs(Eu).max()
+    assert np.max(np.abs(got["E_down"][0] - Ed)) < 1e-12 * scale and np.max(np.abs(got["E_up"][0] - Eu)) < 1e-12 * scale
+    assert Eu[0] > 1.0 and Ed[20] > 1.0                          # a real thermal spectrum, not zeros
+
+
+@needs_ref
+def test_port_reaches_the_reference_equilibrium_for_a_perturbed_member(port, golden, golden_eq):
+    """The C port over 6,000 iterations == the unmodified reference (tests/golden/ref_equilibrium.npz), bit for bit, for the
+    most strongly perturbed member of the fixture (T_surface 297.8 K at equilibrium)."""
+    c = int(np.argmax(golden_eq["Tsurf"]))
+    assert c not in (0, 14, 15)
+    r = port.advance(port.load_rcmtab(table_path(100)), golden["plevel"], golden["rel_hum"][c:c + 1], float(golden["solar_irr"]),
+                     golden["Tlayer"][c:c + 1], golden["Tsurf"][c:c + 1], golden["vmr9"][c:c + 1], int(golden_eq["nsteps"]))
+    assert np.array_equal(r["Tlayer"][0], golden_eq["Tlayer"][c]) and r["Tsurf"][0] == golden_eq["Tsurf"][c]

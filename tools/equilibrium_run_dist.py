@@ -76,7 +76,9 @@ if rank == 0:
                       "converged_fraction": res["converged_fraction"], "max_dT": res["max_dT"],
                       "toa_net_mean_Wm2": res["toa_net_mean"], "Tsurf_mean": float(tsum[0]) / ncol,
                       "Tsurf_min": -float(tsum[1]), "Tsurf_max": float(tsum[2]),
-                      "member0_Tsurf": float(out["Tsurf"][0])}))
+                      "member0_Tsurf": float(out["Tsurf"][0]),
+                      # per-column results do not depend on the sharding: the same value for every N (split path)
+                      "T_sha_first64": __import__("hashlib").sha256(out["Tlayer"][:64].tobytes()).hexdigest()[:16]}))
 s.close()
 if world > 1:
     rdist.barrier()
