@@ -79,46 +79,64 @@ def build_ensemble(rcm, ncol, seed):
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """ONE nvidia-smi process (on rank 0) samples clocks / throttle reasons of the first `ngpu` GPUs every 50 ms.  It is
+    started well before the timed region (nvidia-smi needs a while to deliver its first row, longer with 8 GPUs);
+    window() marks the timed region, stop() evaluates the rows that arrived inside it."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, ngpu):
+        self.ngpu, self.rows, self.proc, self.t0, self.t1 = ngpu, [], None, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def wait_first(self, timeout=10.0):
+        t = time.time()
+        while self.proc is not None and not self.rows and time.time() - t < timeout:
+            time.sleep(0.02)
+
+    def window(self, t0, t1):
+        self.t0, self.t1 = t0, t1
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        per = {}
+        mx, reasons, n_in = None, set(), 0
+        # rows of the timed region (one sampling period of slack on both sides: a row describes the 50 ms before it)
+        for ts, r in self.rows:
             try:
-                sm.append(float(r[0]))
-                mx = float(r[1])
+                idx, sm, mxr = int(r[0]), float(r[1]), float(r[2])
             except (ValueError, IndexError):
                 continue
-            for nm, v in zip(names, r[3:7]):
+            if idx >= self.ngpu or (self.t0 is not None and not (self.t0 - 0.01 <= ts <= self.t1 + 0.06)):
+                continue
+            n_in += 1
+            mx = mxr
+            per.setdefault(idx, []).append(sm)
+            for nm, v in zip(names, r[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
-        busy = [x for x in sm if mx and x > 0.5 * mx] or sm
+        med = {i: statistics.median([x for x in v if mx and x > 0.5 * mx] or v) for i, v in per.items()}
+        allv = [x for v in per.values() for x in v]
+        busy = [x for x in allv if mx and x > 0.5 * mx] or allv
         return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": n_in, "per_gpu_sm_mhz": {"min": min(med.values()), "max": max(med.values())} if med else None,
+                "gpus_sampled": len(per)}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -297,6 +315,10 @@ def run_b200(args, rank, world, local_rank):
     nwvl = solver.nwvl
     units_per_step = ncol * nwvl * NLAY
 
+    sampler = None
+    if rank == 0:  # one nvidia-smi for all the GPUs of the job, started long before the timed region
+        sampler = ClockSampler(world)
+        sampler.start()
     peaks = {}
     if rank == 0:
         for i, nm in enumerate(("dfma", "exp", "div", "exp_solver")):
@@ -313,20 +335,21 @@ def run_b200(args, rank, world, local_rank):
         one_step()
     exch.latest()  # also loads the handful of torch kernels the read-out uses before the clock starts
     torch.cuda.synchronize()
+    if sampler is not None:
+        sampler.wait_first()
     solver.kernel_time_ms(reset=True)
     l0 = solver.launch_count()
-    sampler = ClockSampler(local_rank)  # every rank watches its own GPU
-    sampler.start()
+    t_w0 = time.time()
     ms_total, scal = timed_loop(torch, rdist, stream, world, args.steps, one_step, exch.latest)
     toa_mean = float(scal[0]) / (world * ncol)
-    clocks = sampler.stop()
+    clocks = None
+    if sampler is not None:
+        sampler.window(t_w0, time.time())
+        clocks = sampler.stop()
     launches = solver.launch_count() - l0
     k_ms, k_n = solver.kernel_time_ms(reset=True)
     value = world * units_per_step * args.steps / (ms_total * 1e-3)
     k_ms_ranks = gather_floats(rdist, torch, k_ms, world)
-    sm_ranks = gather_floats(rdist, torch, clocks["sm_mhz"] or 0.0, world)
-    throttle_ranks = gather_floats(rdist, torch, float(len([r for r in clocks["reasons"] if r != "sw_power_cap"])), world)
-    pcap_ranks = gather_floats(rdist, torch, float("sw_power_cap" in clocks["reasons"]), world)
 
     # ---- parity of THIS run against the oracle (rank 0, 64 seeded members, all the steps done so far) ------------
     parity = oracle_parity(rcm, st, solver, args.warmup + args.steps, nwvl) if rank == 0 and not args.no_parity else None
@@ -436,9 +459,6 @@ def run_b200(args, rank, world, local_rank):
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
                "sample": f"{args.cpu_cols} columns x {args.cpu_steps} steps per core, one process per core, "
                          f"table cached in RAM ({walls[0]:.1f} s wall)"}
-    clocks["per_rank_sm_mhz"] = {"min": min(sm_ranks), "max": max(sm_ranks)}
-    clocks["ranks_throttled"] = int(sum(1 for x in throttle_ranks if x > 0))
-    clocks["ranks_power_capped"] = int(sum(pcap_ranks))
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
@@ -609,13 +629,13 @@ def run_b200_lbl(args, rank, world, local_rank):
         rdist.init("nccl")
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(world)
     if rank == 0:
         sampler.start()
     line = lbl_block(args, rank, world, local_rank, torch, rcm, rdist, stream, args.steps)
     if rank != 0:
         return 0
-    line["clocks"] = sampler.stop()
+    line["clocks"] = sampler.stop()  # the whole block (no window): warm-up, timed steps, e2e leg
     print(json.dumps(line), flush=True)
     return 0
 

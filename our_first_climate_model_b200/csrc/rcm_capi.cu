@@ -31,6 +31,7 @@ struct rcm_solver {
     int opt_path = 0;          // 0: split path (tile x wavelength-split units) when it applies; 1: fused tile kernel
     int opt_cplk_narrow = 0;   // rcm_cplkavg_device evaluates the LBL kernel's narrow-band variant (tests)
     double tau_clamp = 240.0;  // set by build_angles
+    double T_floor = 0.0;      // set by rcm_set_spectral_grid: max over the grid of h*c/(lambda*kB) / 690
     int clampk = 1;
     // table
     bool has_table = false, has_spectral = false;
@@ -77,7 +78,7 @@ struct rcm_solver {
     // ... of the split path: uploads + K5 prep (high priority), unit kernels alternating on two streams, K5 finish + downloads
     // (high priority); one event per chunk and stage
     cudaStream_t sp_up = nullptr, sp_rt[2] = {nullptr, nullptr}, sp_down = nullptr;
-    cudaEvent_t sp_prep[8] = {}, sp_rtdone[8] = {}, sp_end = nullptr;
+    cudaEvent_t sp_prep[16] = {}, sp_rtdone[16] = {}, sp_end = nullptr;
     double kt_ms = 0.0;
     long kt_n = 0;
 };
@@ -411,6 +412,7 @@ int launch_part(rcm_solver* s, int mode, int nsteps, bool want_diag, const Part&
     a.clampk = s->clampk;
     a.stage_rows = s->opt_stage_rows;
     a.tau_clamp = s->tau_clamp;
+    a.T_floor = s->T_floor;
     a.nsteps = nsteps;
     a.step_index = s->step_index;
     a.coef = s->d_coef;
@@ -497,6 +499,7 @@ SplitArgs split_args(rcm_solver* s, int col0, int ncols, int which) {
     a.clampk = s->clampk;
     a.h2o_slot = s->h2o_slot;
     a.tau_clamp = s->tau_clamp;
+    a.T_floor = s->T_floor;
     a.coef = s->d_coef;
     a.planck_c = s->d_planck_c;
     a.planck_k = s->d_planck_k;
@@ -638,7 +641,7 @@ int step_host_split(rcm_solver* s, int nchunk, const double* Tlayer_in, const do
         CU(cudaStreamCreateWithPriority(&s->sp_up, cudaStreamNonBlocking, hi));
         CU(cudaStreamCreateWithPriority(&s->sp_down, cudaStreamNonBlocking, hi));
         for (int i = 0; i < 2; ++i) CU(cudaStreamCreateWithPriority(&s->sp_rt[i], cudaStreamNonBlocking, lo));
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 16; ++i) {
             CU(cudaEventCreateWithFlags(&s->sp_prep[i], cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&s->sp_rtdone[i], cudaEventDisableTiming));
         }
@@ -768,7 +771,7 @@ int rcm_destroy(rcm_solver* s) {
     if (s->pipe_start) cudaEventDestroy(s->pipe_start);
     for (cudaStream_t q : {s->sp_up, s->sp_rt[0], s->sp_rt[1], s->sp_down})
         if (q) cudaStreamDestroy(q);
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < 16; ++i) {
         if (s->sp_prep[i]) cudaEventDestroy(s->sp_prep[i]);
         if (s->sp_rtdone[i]) cudaEventDestroy(s->sp_rtdone[i]);
     }
@@ -878,11 +881,21 @@ int rcm_set_spectral_grid(rcm_solver* s, const double* wvl, const double* weight
     //   B = w*2*h*c^2 / (lambda^5 * (exp(h*c/(lambda*kB*T)) - 1)) / 1e9
     const double h = 6.62607e-34, c = 299792458, kB = 1.380649e-23;  // main.cpp:70-72
     std::vector<double> pc(n_wvl), pk(n_wvl);
+    double pc_max = 0.0;
     for (int i = 0; i < n_wvl; ++i) {
         const double lam = wvl[i] * 1e-9;
         pc[i] = h * c / (lam * kB);
         pk[i] = weight[i] * 2 * h * std::pow(c, 2) / std::pow(lam, 5) / 1e9;
+        if (!(wvl[i] > 0.0) || !std::isfinite(pk[i])) return fail(s, RCM_ERR_ARG, "wavelengths must be positive and finite");
+        pc_max = std::max(pc_max, pc[i]);
     }
+    // The kernels' exp (exp_scaled) takes exponents up to ~700 and has no overflow path: the Planck exponent
+    // h*c/(lambda*kB*T) is kept below 690 by evaluating the source at max(T, T_floor), T_floor = max(h*c/(lambda*kB)) / 690
+    // (5.1 K for the repwvl tables; the reference's exp overflows to inf there and its source is 0 - here it is < 1e-299
+    // of the Planck factor).  A grid whose floor would reach atmospheric temperatures is refused: this is the thermal path.
+    if (pc_max / 690.0 > 20.0)
+        return fail(s, RCM_ERR_ARG, "wavelengths below 1043 nm are not supported (thermal solver: the Planck exponent would leave the range of the kernels' exp)");
+    s->T_floor = pc_max / 690.0;
     CU(dalloc(s->d_planck_c, (size_t)n_wvl));
     CU(dalloc(s->d_planck_k, (size_t)n_wvl));
     CU(cudaMemcpy(s->d_planck_c, pc.data(), n_wvl * sizeof(double), cudaMemcpyHostToDevice));
@@ -1384,7 +1397,9 @@ int rcm_load_checkpoint(rcm_solver* s, const char* path) {
 int rcm_step_host(rcm_solver* s, const double* Tlayer_in, const double* Tsurf_in, const double* vmr_active_in,
                   double* E_down, double* E_up, double* dE, double* Tlayer_out, double* Tsurf_out) {
     if (!s) return RCM_ERR_ARG;
-    const int nchunk = (s && !s->lbl_mode && s->has_table) ? std::min(8, s->ncol / 4096) : 0;
+    int max_chunks = 8;
+    if (const char* e = std::getenv("RCM_PIPE_CHUNKS")) max_chunks = std::max(1, std::min(16, std::atoi(e)));  // experiments
+    const int nchunk = (s && !s->lbl_mode && s->has_table) ? std::min(max_chunks, s->ncol / 4096) : 0;
     if (nchunk < 2) {
         int st = rcm_update_columns(s, Tlayer_in, Tsurf_in, vmr_active_in);
         if (st != RCM_OK) return st;

@@ -71,6 +71,7 @@ struct StepArgs {
     int stage_rows;      // 1: the next wavelength's table rows travel into shared memory (cp.async) during the angle loop
     int clampk;          // 1: exp_scaled clamps its exponent itself (angle schedules where tau_clamp would bite)
     double tau_clamp;    // tau is clamped to this before the transmissions are evaluated (see exp_scaled)
+    double T_floor;      // the Planck source is evaluated at max(T, T_floor): keeps exp_scaled's exponent in range (rcm_set_spectral_grid)
     int ntiles;
     int nsteps;          // time steps fused in this launch
     long step_index;     // global index of the first step (0 => initial-profile tau, main.cpp:500-504)
@@ -126,7 +127,7 @@ struct SplitArgs {
     int diag_ncol;       // columns of the whole ensemble = row length of diag
     int ntiles, nsplit, ipu, nitem, nunits;  // tiles of 16 columns; splits per tile; wavelength rounds per split / per tile
     int stage_rows, clampk, h2o_slot;
-    double tau_clamp;
+    double tau_clamp, T_floor;  // as StepArgs
     const double* __restrict__ coef;
     const double* __restrict__ planck_c;
     const double* __restrict__ planck_k;

@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(SPLIT_COL_NT, 8) rcm_split_col_kernel(const Sp
     constexpr int C = SPLIT_C, NT = SPLIT_COL_NT, LC = NLAY * C;
     __shared__ double sT[LC], sTh[LC], sPrev[LC], sRh[LC], sEd[NLEV * C], sEu[NLEV * C], sdE[LC], sdt[C], sTs[C], sSol[C], sStat[C];
     __shared__ int sit[LC], sitmin[NLAY], sout[NLAY + 1];
+    int extrap = 0;  // some temperature of the tile lies outside the table's nodes: cross sections are extrapolated
     const int tid = threadIdx.x, tile = blockIdx.x;
     const int col0 = tile * C, ncl = min(C, a.ncol - col0);
     const int nact = cst.nactive, nwvl = cst.nwvl;
@@ -155,6 +156,7 @@ __global__ void __launch_bounds__(SPLIT_COL_NT, 8) rcm_split_col_kernel(const Sp
             const double midT = sT[i], tref = cst.tref_ip[r];
             const int it = lowerpos_t(tref, midT, cst.n_tpert);
             const double t0 = tref + cst.t_pert[it], t1 = tref + cst.t_pert[it + 1];
+            extrap |= (midT < tref + cst.t_pert[0]) | (midT > tref + cst.t_pert[cst.n_tpert - 1]);
             sit[r * C + cc] = it;
             tbi[TBI_IT + r * C + cc] = it;
             tb[TB_DELT + r * C + cc] = (midT - t0) / (t1 - t0);
@@ -211,12 +213,13 @@ __global__ void __launch_bounds__(SPLIT_COL_NT, 8) rcm_split_col_kernel(const Sp
         tb[TB_VMR + (sp * NLAY + prow(l)) * C + cc] = v;
     }
     if (!f.first) indices();
-    for (int i = tid; i < LC; i += NT) tb[TB_INVT + prow(i / C) * C + i % C] = (1.0 / sT[i]) * L2E64;
+    // (T_floor: a column colder than ~5 K would take the fast exp's exponent out of range - its source is 0 either way)
+    for (int i = tid; i < LC; i += NT) tb[TB_INVT + prow(i / C) * C + i % C] = (1.0 / fmax(sT[i], a.T_floor)) * L2E64;
     if (tid < C) {
-        tb[TB_INVTS + tid] = (1.0 / sTs[tid]) * L2E64;
+        tb[TB_INVTS + tid] = (1.0 / fmax(sTs[tid], a.T_floor)) * L2E64;
         tb[TB_CLOUD + tid] = a.cloud_col ? a.cloud_col[col0 + (tid < ncl ? tid : 0)] : cst.cloud_tau;
     }
-    __syncthreads();
+    const int any_extrap = __syncthreads_or(extrap);
     // the candidate rows of every layer: temperature intervals it_min .. it_min + NCAND - 1 of the tile's columns
     if (tid < NLAY) {
         int mn = sit[tid * C], mx = mn;
@@ -234,7 +237,9 @@ __global__ void __launch_bounds__(SPLIT_COL_NT, 8) rcm_split_col_kernel(const Sp
         tbi[TBI_ROWSEL + i] = (NCAND * r + min(sit[i] - sitmin[r], NCAND - 1)) * ROWB;
     }
     if (tid == 0) {
-        int any = 0;
+        // extrapolated cross sections can come out negative: such a tile also takes the global-memory K1, which clamps
+        // tau from below so that the transmissions' exp stays in range (the staged K1 of ordinary tiles pays nothing)
+        int any = any_extrap;
         for (int r = 0; r < NLAY; ++r) any |= sout[r];
         tbi[TBI_OUTSIDE] = any;
     }
@@ -303,13 +308,15 @@ __global__ void __launch_bounds__(SPLIT_NT, 3) rcm_split_rt_kernel(const SplitAr
     if (tid == 0) {
         mbar_init(mbar, 1);
         const int u = (int)atomicAdd(a.counter, 1u);
-        *s_next = u;
+        s_next[0] = u;
+        s_next[1] = 1;
         if (u < a.nunits) tma_load_1d(tb_addr, a.tile + (size_t)(u / a.nsplit) * TILE_BYTES, TILE_BYTES, mbar);
     }
     __syncthreads();
     int unit = *s_next;
     unsigned phase = 0;
-    int taken = 1;  // units this CTA has taken from the counter (a.quota: it leaves its slot to waiting kernels after that many)
+    // s_next[1]: units this CTA has taken from the counter (a.quota: it leaves its slot to waiting kernels after that many);
+    // kept in shared memory - thread 0 alone needs it, once per unit, and the kernel has no register to spare
 
     auto request_rows = [&](int w) {  // as in the fused kernel: 60 rows of wavelength w, lane q copies rows q and q + 32
         __syncwarp();
@@ -371,7 +378,7 @@ __global__ void __launch_bounds__(SPLIT_NT, 3) rcm_split_rt_kernel(const SplitAr
                 for (int j = 0; j < HALF; ++j) {
                     const int cell = cst.ipcell[h * HALF + j] + tbi[TBI_IT + sb + j * C];
                     const double v = tau_from(j, reinterpret_cast<const double2*>(a.coef) + (size_t)(cell * nwvl + w) * 2 * NACT, cl);
-                    tau[j] = CLAMPK ? v : fmin(v, a.tau_clamp);
+                    tau[j] = fmax(CLAMPK ? v : fmin(v, a.tau_clamp), TAU_FLOOR);
                 }
             }
             // K2: Planck source B = k_w / (exp(c_w / T) - 1) (main.cpp:188-191, wavelength-only factors from the host)
@@ -396,11 +403,12 @@ __global__ void __launch_bounds__(SPLIT_NT, 3) rcm_split_rt_kernel(const SplitAr
         }
         __syncthreads();  // nobody reads the tile block any more: the next unit's block may land
         if (tid == 0) {
+            const int taken = s_next[1];
             const int u = (taken < a.quota) ? (int)atomicAdd(a.counter, 1u) : a.nunits;
-            *s_next = u;
+            s_next[0] = u;
+            s_next[1] = taken + 1;
             if (u < a.nunits) tma_load_1d(tb_addr, a.tile + (size_t)(u / a.nsplit) * TILE_BYTES, TILE_BYTES, mbar);
         }
-        ++taken;
         double* out = a.part + (size_t)unit * SPLIT_PART;
         for (int i = tid; i < SPLIT_PART; i += NT) {
             double sum = 0.0;

@@ -133,6 +133,7 @@ __device__ __forceinline__ void sweep_item(const double (&tau)[HALF], const doub
 // arrays are stored in this order: row(l) = l for l<10, 29-l otherwise (= 10*h + j).
 __device__ __forceinline__ constexpr int prow(int l) { return l < HALF ? l : 29 - l; }
 
+constexpr double TAU_FLOOR = -8.0;       // lower clamp of tau in front of the transmissions: exp(8 * 60) is still in range
 constexpr int ROWB = 5 * 32;             // bytes of one table row: 5 active species x {c0, cT, cP, cPT}
 constexpr int NCAND = 3;                 // candidate rows per layer: temperature intervals it_min .. it_min + 2 of the tile
 constexpr int ROWBUF = NLAY * NCAND * ROWB;  // per warp: 60 rows, 9600 bytes
@@ -339,7 +340,11 @@ __global__ void __launch_bounds__(NT, min_ctas(NT)) rcm_step_kernel(const StepAr
                 v = tau_cell(j, w, cl);
             }
             if (!CLAMPK) v = fmin(v, a.tau_clamp);  // exp(-tau_clamp/mu) ~ 1e-100: same fluxes, see exp_scaled
-            return v;
+            return fmax(v, TAU_FLOOR);  // a negative tau (cross sections extrapolated far outside the table) must not overflow the exp
+        };
+        auto tau_staged_use = [&](int j, double cl) -> double {
+            const double v = tau_staged(j, cl);
+            return fmax(CLAMPK ? v : fmin(v, a.tau_clamp), TAU_FLOOR);
         };
 
         for (int step = 0; step < a.nsteps; ++step) {
@@ -406,8 +411,8 @@ __global__ void __launch_bounds__(NT, min_ctas(NT)) rcm_step_kernel(const StepAr
             } else if (MODE == MODE_TAU) {
                 prep_tau_indices(s, tid);
             }
-            for (int i = tid; i < NLAY * C; i += NT) s.invT[i] = 1.0 / s.T[i];
-            if (tid < C) s.invTs[tid] = 1.0 / s.Ts[tid];
+            for (int i = tid; i < NLAY * C; i += NT) s.invT[i] = 1.0 / fmax(s.T[i], a.T_floor);
+            if (tid < C) s.invTs[tid] = 1.0 / fmax(s.Ts[tid], a.T_floor);
             __syncthreads();
             if (stage) {
                 // the candidate rows of every layer: temperature intervals it_min .. it_min + 2 of the tile's columns
@@ -478,10 +483,7 @@ __global__ void __launch_bounds__(NT, min_ctas(NT)) rcm_step_kernel(const StepAr
                 // a tile where some column needs a row beyond the two candidates takes the global one for every layer
                 if (stage && !s.outside[NLAY]) {
 #pragma unroll
-                    for (int j = 0; j < HALF; ++j) {
-                        const double v = tau_staged(j, cl);
-                        tau[j] = CLAMPK ? v : fmin(v, a.tau_clamp);
-                    }
+                    for (int j = 0; j < HALF; ++j) tau[j] = tau_staged_use(j, cl);
                 } else {
 #pragma unroll
                     for (int j = 0; j < HALF; ++j) tau[j] = tau_use(j, w, cl);

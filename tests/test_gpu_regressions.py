@@ -78,3 +78,40 @@ def test_checkpoint_refuses_another_wavelength_count(rcm, golden, tmp_path):
         s.advance(1)
     finally:
         s.close()
+
+
+def test_planck_exponent_stays_in_range(rcm, golden):
+    """The kernels' exp has no overflow path (robustness): a runaway cold column (2 K) must give finite - zero -
+    thermal emission like the reference's exp -> inf -> B = 0, not a wrapped exponent; a spectral grid that would put the
+    Planck exponent out of range at atmospheric temperatures (wavelengths below ~1 um) is refused at the ABI."""
+    s = rcm.Solver(0)
+    try:
+        s.set_repwvl_table_from(rcm.Table(table_path(20)))
+        T = golden["Tlayer"][:3].copy()
+        T[1, :] = 2.0
+        T[2, 5] = 0.5
+        Ts = np.array([288.2, 2.0, 288.2])
+        for path in (0, 1):
+            s.set_option(5, path)
+            s.set_columns(golden["plevel"], T, Ts, golden["vmr9"][:3], golden["rel_hum"][:3])
+            tau, _, _ = s.build_tau()
+            s.update_columns(Tlayer=T, Tsurf=Ts)
+            Ed, Eu, dE = s.radiative_transfer(np.clip(tau, 0, None))
+            assert np.isfinite(Ed).all() and np.isfinite(Eu).all() and np.isfinite(dE).all()
+            # nothing radiates at 2 K; the source is evaluated at T_floor = 5.1 K: below a 5 K blackbody's 3.8e-5 W/m2
+            assert np.all(np.abs(Eu[1]) < 1e-5) and np.all(np.abs(Ed[1]) < 1e-5)
+            assert Eu[2, 0] > 50.0 and Eu[0, 0] > 50.0
+            s.set_columns(golden["plevel"], T, Ts, golden["vmr9"][:3], golden["rel_hum"][:3])
+            s.advance(1)
+            st = s.get_state()
+            # (in the full step the 2 K column's cross sections are extrapolated 100 K below the table and come out negative:
+            # its fluxes are meaningless - amplified by exp(+8/mu) per layer, inf / NaN in the reference too; its neighbours in
+            # the tile are untouched)
+            assert np.isfinite(st["E_up"][[0, 2]]).all() and np.isfinite(st["Tlayer"][[0, 2]]).all()
+            assert abs(st["E_up"][0, 0] - golden["s1_E_up_20"][0, 0]) < 1e-10 * st["E_up"][0, 0]
+        s.set_option(5, 0)
+        with pytest.raises(rcm.RcmError, match="1043"):
+            s.set_spectral_grid(np.array([500.0, 5000.0]), np.array([1.0, 1.0]))
+        s.set_spectral_grid(np.array([1100.0, 5000.0]), np.array([1.0, 1.0]))
+    finally:
+        s.close()
