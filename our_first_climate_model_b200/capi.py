@@ -35,7 +35,8 @@ class StepScalars(C.Structure):
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, "lib", "librcm_b200.so")
+    # RCM_B200_LIB: another build of the same library (kernel variants under test: tools/build_variants.sh)
+    return os.environ.get("RCM_B200_LIB") or os.path.join(_HERE, "lib", "librcm_b200.so")
 
 
 def header_path() -> str:

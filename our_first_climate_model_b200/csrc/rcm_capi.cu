@@ -78,7 +78,7 @@ struct rcm_solver {
     // ... of the split path: uploads + K5 prep (high priority), unit kernels alternating on two streams, K5 finish + downloads
     // (high priority); one event per chunk and stage
     cudaStream_t sp_up = nullptr, sp_rt[2] = {nullptr, nullptr}, sp_down = nullptr;
-    cudaEvent_t sp_prep[16] = {}, sp_rtdone[16] = {}, sp_end = nullptr;
+    cudaEvent_t sp_prep[24] = {}, sp_rtdone[24] = {}, sp_end = nullptr;
     double kt_ms = 0.0;
     long kt_n = 0;
 };
@@ -641,7 +641,7 @@ int step_host_split(rcm_solver* s, int nchunk, const double* Tlayer_in, const do
         CU(cudaStreamCreateWithPriority(&s->sp_up, cudaStreamNonBlocking, hi));
         CU(cudaStreamCreateWithPriority(&s->sp_down, cudaStreamNonBlocking, hi));
         for (int i = 0; i < 2; ++i) CU(cudaStreamCreateWithPriority(&s->sp_rt[i], cudaStreamNonBlocking, lo));
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < 24; ++i) {
             CU(cudaEventCreateWithFlags(&s->sp_prep[i], cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&s->sp_rtdone[i], cudaEventDisableTiming));
         }
@@ -649,13 +649,27 @@ int step_host_split(rcm_solver* s, int nchunk, const double* Tlayer_in, const do
     }
     const int nsm = nsm_of(s);
     const int per = ((s->ncol + nchunk - 1) / nchunk + 15) / 16 * 16;
+    // chunk boundaries (whole tiles): the first and the last chunk are quarter-sized, their neighbours three quarters - the
+    // upload of the first chunk and the download of the last one are the only copies nothing overlaps
+    int bounds[24];
+    int nb = 0;
+    bounds[nb++] = 0;
+    if (nchunk >= 4 && per >= 64) {
+        const int q = per / 4 / 16 * 16;
+        bounds[nb++] = q;
+        for (int c0 = per; c0 < s->ncol - q; c0 += per) bounds[nb++] = c0;
+        bounds[nb++] = std::max(bounds[nb - 1], s->ncol - q) / 16 * 16;
+    } else {
+        for (int c0 = per; c0 < s->ncol; c0 += per) bounds[nb++] = c0;
+    }
+    bounds[nb] = s->ncol;
     CU(cudaEventRecord(s->sp_end, s->stream));  // everything queued on the solver's stream so far comes first
     for (cudaStream_t q : {s->sp_up, s->sp_rt[0], s->sp_rt[1], s->sp_down}) CU(cudaStreamWaitEvent(q, s->sp_end, 0));
     const size_t D = sizeof(double);
     const int na = s->nactive;
-    int k = 0;
-    for (int c0 = 0; c0 < s->ncol; ++k, c0 += per) {
-        const int n = std::min(per, s->ncol - c0);
+    for (int k = 0; k < nb; ++k) {
+        const int c0 = bounds[k], n = bounds[k + 1] - c0;
+        if (n <= 0) continue;
         const size_t o = (size_t)c0;
         cudaStream_t q = s->sp_up;
         if (Tlayer_in) CU(cudaMemcpyAsync(s->d_T + o * NLAY, Tlayer_in + o * NLAY, n * NLAY * D, cudaMemcpyHostToDevice, q));
@@ -771,7 +785,7 @@ int rcm_destroy(rcm_solver* s) {
     if (s->pipe_start) cudaEventDestroy(s->pipe_start);
     for (cudaStream_t q : {s->sp_up, s->sp_rt[0], s->sp_rt[1], s->sp_down})
         if (q) cudaStreamDestroy(q);
-    for (int i = 0; i < 16; ++i) {
+    for (int i = 0; i < 24; ++i) {
         if (s->sp_prep[i]) cudaEventDestroy(s->sp_prep[i]);
         if (s->sp_rtdone[i]) cudaEventDestroy(s->sp_rtdone[i]);
     }

@@ -268,3 +268,16 @@ def test_cplkavg_exact_signature_against_the_reference_build(golden_misc):
     for exe in (ref, mine):
         r = subprocess.run([exe], input="500 400 300\n", capture_output=True, text=True, timeout=60)
         assert r.returncode == 1 and "planck_func1--temperature or wavenums. wrong" in r.stderr
+
+
+def test_roofline_constants_belong_to_the_committed_kernels():
+    """bench.py computes `roofline.frac` from FP64-instruction counts taken out of ncu captures (profiles/roofline_capture.json).
+    The captures are only valid for the kernel sources they were taken on: the json records their sha256, and this test fails
+    when a kernel source has moved since - re-capture (tools/profile_r2.sh) and run tools/update_roofline_capture.py."""
+    import bench
+    cap = bench.load_capture()
+    assert not cap["stale"], ("kernel sources changed after the ncu capture recorded in profiles/roofline_capture.json: "
+                              f"recorded {cap.get('sources_sha256')}, now {cap['current_sha']}")
+    for w in ("step", "lbl"):
+        assert 200 < cap[w]["exec_fp64_per_unit"] < 600 and cap[w]["kernel"].find("rcm_") >= 0
+    assert "rcm_split_rt_kernel" in cap["step"]["kernel"] and cap["step"]["ncol"] == 65536 and cap["step"]["nwvl"] == 100
