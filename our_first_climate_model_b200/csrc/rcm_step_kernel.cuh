@@ -224,6 +224,9 @@ __device__ __forceinline__ void prep_tau_indices(const Smem<C, NT, NACT>& s, int
         const double tref = cst.tref_ip[r];
         const int it = lowerpos_t(tref, midT, cst.n_tpert);
         const double t0 = tref + cst.t_pert[it], t1 = tref + cst.t_pert[it + 1];
+        // outside the table's temperature nodes the cross sections are extrapolated and can come out negative: such a
+        // tile takes the global-memory K1, the variant that clamps tau from below (benign race: everybody writes 1)
+        if (midT < tref + cst.t_pert[0] || midT > tref + cst.t_pert[cst.n_tpert - 1]) s.outside[NLAY + 1] = 1;
         s.it[i] = it;
         s.delT[i] = (midT - t0) / (t1 - t0);
     }
@@ -243,6 +246,7 @@ __global__ void __launch_bounds__(NT, min_ctas(NT)) rcm_step_kernel(const StepAr
     const int sb = h * HALF * C + c;  // this thread's row block in the per-layer arrays
 
     for (int i = tid; i < EXP_TAB * EXP_REP; i += NT) s.exp_tab[i] = a.exp_tab[i / EXP_REP];
+    if (tid == 0) s.outside[NLAY + 1] = 0;
     const unsigned tab_lane = (unsigned)__cvta_generic_to_shared(s.exp_tab + (lane & (EXP_REP - 1)));
     const int nwvl = cst.nwvl;
     // Planck factors of a repwvl-sized table live in shared memory (the per-wavelength global loads sat on the long
@@ -344,7 +348,7 @@ __global__ void __launch_bounds__(NT, min_ctas(NT)) rcm_step_kernel(const StepAr
         };
         auto tau_staged_use = [&](int j, double cl) -> double {
             const double v = tau_staged(j, cl);
-            return fmax(CLAMPK ? v : fmin(v, a.tau_clamp), TAU_FLOOR);
+            return CLAMPK ? v : fmin(v, a.tau_clamp);
         };
 
         for (int step = 0; step < a.nsteps; ++step) {
@@ -433,7 +437,8 @@ __global__ void __launch_bounds__(NT, min_ctas(NT)) rcm_step_kernel(const StepAr
                     s.rowsel[i] = (NCAND * r + min(s.it[i] - s.itmin[r], NCAND - 1)) * ROWB;
                 }
                 if (tid == 0) {
-                    int any = 0;
+                    int any = s.outside[NLAY + 1];  // extrapolation flag of prep_tau_indices, consumed here
+                    s.outside[NLAY + 1] = 0;
                     for (int r = 0; r < NLAY; ++r) any |= s.outside[r];
                     s.outside[NLAY] = any;
                 }
