@@ -96,3 +96,27 @@ def test_lbl_wavelength_chunking_is_deterministic(rcm, lbl_case):
         b = got[k].reshape(rep, n, -1)
         assert np.array_equal(b[0], b[-1]) and np.array_equal(b[0], b[rep // 2])
     s.close()
+
+
+def test_lbl_shards_are_bit_identical_to_the_whole_ensemble(rcm, lbl_case):
+    """The LBL spectral sum runs over fixed 128-wavelength chunks (registers over a chunk's rounds, groups, chunks in
+    index order): independent of how many columns a GPU owns.  The ensemble stepped as a whole and as three sequential
+    shards gives the same bytes (round 1 sized the chunks from the column count: another summation order per shard)."""
+    from our_first_climate_model_b200.distributed import shard_range
+    c, st = lbl_case, lbl_case["st"]
+    n = c["ncol"]
+
+    def run(lo, hi):
+        s = rcm.Solver(0)
+        s.set_lbl_tables(c["wvl"], c["tau5"], c["h2o_ref"], c["o3_ref"], 2.0)
+        s.set_columns(c["pl"], st["Tlayer"][lo:hi], c["Tsurf"][lo:hi], st["vmr9"][lo:hi], st["rel_hum"][lo:hi])
+        s.advance(1)
+        s.advance(2)
+        out = s.get_state()
+        s.close()
+        return out
+
+    whole = run(0, n)
+    parts = [run(*shard_range(n, r, 3)) for r in range(3)]
+    for k in ("E_up", "E_down", "dE", "Tlayer", "Tsurf", "h2o", "dt"):
+        assert np.array_equal(np.concatenate([p[k] for p in parts]), whole[k]), k
