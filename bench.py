@@ -216,9 +216,10 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": dict(workload_config(args.ncol, args.nwvl, args.gpus),
-                           sample=f"each bench step = {cols} columns x 1 reference iteration (main.cpp:531-583) per "
-                                  f"host core, a bounded sample of that workload"),
+            # the same `config` as this repo's arm; what a bench step of this arm is: see cpu_baseline.sample
+            "config": workload_config(args.ncol, args.nwvl, args.gpus),
+            "sample": f"each bench step = {cols} columns x 1 reference iteration (main.cpp:531-583) per host core, a bounded "
+                      f"sample of that workload",
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "literal_reread": literal},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}

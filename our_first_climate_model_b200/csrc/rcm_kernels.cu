@@ -346,6 +346,6 @@ cudaError_t rcm_launch_lbl_step(const LblArgs& a, cudaStream_t st, cudaEvent_t e
     if (ev0) cudaEventRecord(ev0, st);
     kern<<<a.ntiles * a.nchunks, NT, smem, st>>>(a);
     if (ev1) cudaEventRecord(ev1, st);
-    rcm_lbl_finish_kernel<<<(a.ncol + 127) / 128, 128, 0, st>>>(a);
+    rcm_lbl_finish_kernel<<<a.ncol, LBL_FIN_NT, 0, st>>>(a);
     return cudaGetLastError();
 }
