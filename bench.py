@@ -79,7 +79,7 @@ def build_ensemble(rcm, ncol, seed):
 
 
 class ClockSampler:
-    """ONE nvidia-smi process (on rank 0) samples clocks / throttle reasons of the first `ngpu` GPUs every 50 ms.  It is
+    """ONE nvidia-smi process (on rank 0) samples clocks / throttle reasons of the first `ngpu` GPUs every 20 ms.  It is
     started well before the timed region (nvidia-smi needs a while to deliver its first row, longer with 8 GPUs);
     window() marks the timed region, stop() evaluates the rows that arrived inside it."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -91,7 +91,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -117,7 +117,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         per = {}
         mx, reasons, n_in = None, set(), 0
-        # rows of the timed region (one sampling period of slack on both sides: a row describes the 50 ms before it)
+        # rows of the timed region (one sampling period of slack on both sides: a row describes the 20 ms before it)
         for ts, r in self.rows:
             try:
                 idx, sm, mxr = int(r[0]), float(r[1]), float(r[2])

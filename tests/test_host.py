@@ -281,3 +281,26 @@ def test_roofline_constants_belong_to_the_committed_kernels():
     for w in ("step", "lbl"):
         assert 200 < cap[w]["exec_fp64_per_unit"] < 600 and cap[w]["kernel"].find("rcm_") >= 0
     assert "rcm_split_rt_kernel" in cap["step"]["kernel"] and cap["step"]["ncol"] == 65536 and cap["step"]["nwvl"] == 100
+
+
+def test_clock_sampler_evaluates_only_the_timed_window():
+    """bench.ClockSampler: one nvidia-smi for all GPUs, started before warm-up; only rows that arrived inside the timed
+    window count, per GPU, and throttle reasons of other GPUs / other times do not leak in."""
+    import bench
+
+    class FakeProc:
+        def terminate(self):
+            pass
+
+    s = bench.ClockSampler(2)
+    s.proc = FakeProc()
+    row = lambda idx, sm, *flags: [str(idx), str(sm), "1965", "700.0"] + [("Active" if f else "Not Active") for f in flags]
+    s.rows = [(10.00, row(0, 345, 0, 0, 0, 0)),                      # idle, before the window
+              (10.02, row(0, 1965, 1, 0, 0, 0)),                     # hw_slowdown before the window: must not count
+              (11.00, row(0, 1965, 0, 0, 0, 0)), (11.00, row(1, 1950, 0, 0, 0, 1)), (11.00, row(2, 300, 0, 1, 0, 0)),
+              (11.05, row(0, 1965, 0, 0, 0, 0)), (11.05, row(1, 1935, 0, 0, 0, 1)),
+              (12.00, row(1, 210, 0, 0, 1, 0))]                      # after the window
+    s.window(10.99, 11.06)
+    c = s.stop()
+    assert c["samples"] == 4 and c["gpus_sampled"] == 2 and c["reasons"] == ["sw_power_cap"]
+    assert c["sm_max_mhz"] == 1965.0 and c["per_gpu_sm_mhz"] == {"min": 1942.5, "max": 1965.0}
