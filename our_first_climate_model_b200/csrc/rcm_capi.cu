@@ -234,6 +234,13 @@ void build_angles(rcm_solver* s) {
         const double ec7[4] = {0x1.62e42fefa3685p-8, 0x1.ebfbdff82c58fp-17, 0x1.c6b09b1799fcbp-26, 0x1.3b2ab6fba4e77p-35};
         const double ec10[4] = {0x1.62e42fefa39efp-11, 0x1.ebfbe033445b4p-23, 0x1.c6b08d704a0c0p-35, 0.0};
         for (int k = 0; k < 4; ++k) d.expc[k] = (EXP_LOG2 == 7) ? ec7[k] : ec10[k];
+#ifdef RCM_EXP_DEG_OVERRIDE
+        {   // experiment: plain Taylor coefficients of the shorter polynomial
+            const double c = 0.6931471805599453 / EXP_TAB;
+            const double tay[4] = {c, c * c / 2, c * c * c / 6, c * c * c * c / 24};
+            for (int k = 0; k < 4; ++k) d.expc[k] = (k <= EXP_DEG) ? tay[k] : 0.0;
+        }
+#endif
     }
     // exp_scaled needs |tau/mu|/ln2 <= 1000 for every slot evaluated with exp.  Clamping tau once per layer
     // guarantees that for free - provided the clamped transmission is still zero for every use

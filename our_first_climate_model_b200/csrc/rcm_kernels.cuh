@@ -23,7 +23,11 @@ constexpr int RCM_LBL_C = 16, RCM_LBL_NT = 128;  // tile shape of the LBL radiat
 #endif
 constexpr int EXP_LOG2 = RCM_EXP_LOG2, EXP_TAB = 1 << EXP_LOG2;
 constexpr int EXP_REP = (EXP_LOG2 == 7) ? 8 : 1;
+#ifdef RCM_EXP_DEG_OVERRIDE  // experiments only (tools/build_variants.sh): a shorter Horner polynomial = a less accurate exp
+constexpr int EXP_DEG = RCM_EXP_DEG_OVERRIDE;
+#else
 constexpr int EXP_DEG = (EXP_LOG2 == 7) ? 3 : 2;
+#endif
 static_assert(EXP_LOG2 == 7 || EXP_LOG2 == 10, "exp table configurations: 128 x 8 copies or 1024 x 1");
 constexpr double EXP_L2E = EXP_TAB * 1.4426950408889634;  // EXP_TAB / ln 2: argument scaling of exp_scaled
 
