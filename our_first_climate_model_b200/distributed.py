@@ -85,7 +85,7 @@ class StepScalarExchange:
     With one rank (or no process group) it just keeps references to the local scalars.
     `solver`: when given, every submit() checks that the solver launches on torch's current stream."""
 
-    def __init__(self, device, ring: int = 8, solver=None):
+    def __init__(self, device, ring: int = 32, solver=None):
         self.solver = solver
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.ring = ring
