@@ -36,6 +36,7 @@ struct rcm_solver {
     // table
     bool has_table = false, has_spectral = false;
     std::vector<double> p_grid, t_ref, t_pert, wvl, weight;
+    double* d_coef3 = nullptr;  // the split path's rows (rcm_coef3_kernel), rebuilt with d_coef
     double *d_xsec_file = nullptr, *d_coef = nullptr, *d_planck_c = nullptr, *d_planck_k = nullptr, *d_exp_tab = nullptr;
     int* d_species = nullptr;
     bool coef_dirty = true;
@@ -310,6 +311,12 @@ int refresh_const(rcm_solver* s) {
         CU(cudaMemcpyAsync(s->d_species, s->species, sizeof(s->species), cudaMemcpyHostToDevice, s->stream));
         CU(rcm_launch_coef(s->d_xsec_file, s->d_coef, d.n_tpert, d.n_species, d.nwvl, d.n_p, s->nactive, s->d_species,
                            s->stream));
+        if (s->nactive == 5) {  // the split path's rows
+            const size_t nrows = (size_t)RCM_NLAYER * (d.n_tpert - 1) * d.nwvl;
+            CU(dalloc(s->d_coef3, nrows * 16));
+            CU(rcm_launch_coef3(s->d_coef, s->d_coef3, nrows, s->stream));
+            s->launches += 1;
+        }
         CU(cudaStreamSynchronize(s->stream));
         s->launches += 1;
         s->coef_dirty = false;
@@ -507,7 +514,7 @@ SplitArgs split_args(rcm_solver* s, int col0, int ncols, int which) {
     a.h2o_slot = s->h2o_slot;
     a.tau_clamp = s->tau_clamp;
     a.T_floor = s->T_floor;
-    a.coef = s->d_coef;
+    a.coef = s->d_coef3;
     a.planck_c = s->d_planck_c;
     a.planck_k = s->d_planck_k;
     a.exp_tab = s->d_exp_tab;
@@ -777,7 +784,7 @@ int rcm_destroy(rcm_solver* s) {
     cudaSetDevice(s->device);
     cudaStreamSynchronize(s->stream);
     if (g_const_owner[s->device & 63] == s) g_const_owner[s->device & 63] = nullptr;
-    void* ptrs[] = {s->d_xsec_file, s->d_coef, s->d_species, s->d_planck_c, s->d_planck_k, s->d_exp_tab, s->d_T, s->d_Ts, s->d_vmr, s->d_rh,
+    void* ptrs[] = {s->d_coef3, s->d_xsec_file, s->d_coef, s->d_species, s->d_planck_c, s->d_planck_k, s->d_exp_tab, s->d_T, s->d_Ts, s->d_vmr, s->d_rh,
                     s->d_Tprev, s->d_time, s->d_lbl_lo, s->d_lbl_hi, s->d_lbl_tau5, s->d_lbl_h2o_ref, s->d_lbl_o3_ref, s->d_sH, s->d_sO,
                     s->d_dTstat, s->d_part, s->d_Ed, s->d_Eu, s->d_dE, s->d_dt, s->d_diag, s->d_scalars, s->d_red, s->d_tau,
                     s->d_lowpos, s->d_solar_col, s->d_cloud_col, s->d_ticket, s->d_tile, s->d_spart, s->d_counter};

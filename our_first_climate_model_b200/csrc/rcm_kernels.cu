@@ -60,6 +60,23 @@ __global__ void rcm_coef_kernel(const double* __restrict__ src, double* __restri
     }
 }
 
+// The split path's rows: per (layer row, temperature interval, wavelength) 16 doubles = 128 bytes,
+//   {c0 + cP*delP, cT, cPT} for each of the five species, one pad.
+// Its K1 evaluates x = (c0 + cP*delP) + cT*dT + cPT*(dT*dP) with three FMAs per species (contracted: within 4 ulp of the
+// reference's operation order, which rcm_build_tau / rcm_step_kernel keep bit for bit).
+__global__ void rcm_coef3_kernel(const double* __restrict__ coef4, double* __restrict__ dst, size_t nrows) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nrows * 5; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t row = i / 5;
+        const int k = (int)(i % 5);
+        const double* c = coef4 + (row * 5 + k) * 4;
+        double* d = dst + row * 16 + 3 * k;
+        d[0] = __dadd_rn(c[0], c[2]);
+        d[1] = c[1];
+        d[2] = c[3];
+        if (k == 4) dst[row * 16 + 15] = 0.0;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // Per-step ensemble scalars from the per-column diagnostics.  RED_BLOCKS CTAs per step reduce fixed slices
 // of the columns with a fixed-order tree into partial[step][block][4]; the CTA that finishes last (ticket
@@ -304,6 +321,11 @@ cudaError_t rcm_launch_reduce_diag(const double* diag, int nsteps, int ncol, dou
 cudaError_t rcm_launch_coef(const double* xsec_file, double* coef, int nt, int ns, int nw, int np, int nact,
                             const int* d_species, cudaStream_t st) {
     rcm_coef_kernel<<<296, 256, 0, st>>>(xsec_file, coef, nt, ns, nw, np, nact, d_species);
+    return cudaGetLastError();
+}
+
+cudaError_t rcm_launch_coef3(const double* coef4, double* coef3, size_t nrows, cudaStream_t st) {
+    rcm_coef3_kernel<<<296, 256, 0, st>>>(coef4, coef3, nrows);
     return cudaGetLastError();
 }
 

@@ -132,7 +132,7 @@ struct SplitArgs {
     int ntiles, nsplit, ipu, nitem, nunits;  // tiles of 16 columns; splits per tile; wavelength rounds per split / per tile
     int stage_rows, clampk, h2o_slot;
     double tau_clamp, T_floor;  // as StepArgs
-    const double* __restrict__ coef;
+    const double* __restrict__ coef;      // the split path's rows: [cell][wvl][16] = {c0 + cP*delP, cT, cPT} x 5 species + pad
     const double* __restrict__ planck_c;
     const double* __restrict__ planck_k;
     const double* __restrict__ exp_tab;
@@ -169,6 +169,8 @@ cudaError_t rcm_launch_reduce_diag(const double* diag, int nsteps, int ncol, dou
                                    unsigned* ticket, double* scalars, cudaStream_t st);
 cudaError_t rcm_launch_coef(const double* xsec_file, double* coef, int nt, int ns, int nw, int np, int nact,
                             const int* d_species, cudaStream_t st);
+// coef4: rcm_launch_coef's table for five active species, nrows = 20 * (n_tpert - 1) * nwvl rows -> coef3 [nrows][16]
+cudaError_t rcm_launch_coef3(const double* coef4, double* coef3, size_t nrows, cudaStream_t st);
 cudaError_t rcm_launch_microbench(int which, double* out, const double* tab, long iters, int grid,
                                   cudaStream_t st);
 size_t rcm_lbl_smem_bytes(int C, int nthreads);

@@ -30,7 +30,8 @@ constexpr int SPLIT_COL_NT = 128;  // K5 kernel: 8 CTAs (tiles) per SM at 64 reg
 // the tile block (doubles, then ints); per-layer rows in pair order r = prow(l)
 constexpr int TB_INVT = 0;                               // [20][16]  EXP_L2E / T (sorted profile): Planck exponent factor
 constexpr int TB_DELT = TB_INVT + NLAY * SPLIT_C;        // [20][16]  interpolation weight in T
-constexpr int TB_VMR = TB_DELT + NLAY * SPLIT_C;         // [5][20][16]
+constexpr int TB_DTDP = TB_DELT + NLAY * SPLIT_C;        // [20][16]  that weight times the layer's weight in p (rounded once)
+constexpr int TB_VMR = TB_DTDP + NLAY * SPLIT_C;         // [5][20][16]
 constexpr int TB_INVTS = TB_VMR + 5 * NLAY * SPLIT_C;    // [16]      EXP_L2E / T_surface
 constexpr int TB_CLOUD = TB_INVTS + SPLIT_C;             // [16]
 constexpr int TB_DOUBLES = TB_CLOUD + SPLIT_C;
@@ -41,6 +42,11 @@ constexpr int TBI_OUTSIDE = TBI_ROWOFF + NLAY * NCAND;   // some column needs a 
 constexpr int TB_INTS = (TBI_OUTSIDE + 1 + 3) / 4 * 4;
 constexpr int TILE_BYTES = TB_DOUBLES * 8 + TB_INTS * 4;
 static_assert(TILE_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
+constexpr int ROWB3 = 16 * 8;                   // bytes of one row of the split path's table: 5 species x {c0', cT, cPT} + pad
+// In shared memory the rows are 144 bytes apart: at 128 every row starts at bank 0, and the two lanes of a pair - always
+// on different rows (layers j and 19-j) at the same offset - collide on every LDS.128 (measured: the kernel 14 % slower).
+constexpr int ROWS3 = ROWB3 + 16;
+constexpr int ROWBUF3 = NLAY * NCAND * ROWS3;   // per warp: 60 rows, 8,640 bytes
 constexpr int SPLIT_PART = 2 * NLEV * SPLIT_C;  // doubles of one unit's partial fluxes: rows 0..19 E_down[l+1], 20 unused, 21..41 E_up[l]
 
 // ------------------------------------------------------------------------------------------
@@ -159,7 +165,9 @@ __global__ void __launch_bounds__(SPLIT_COL_NT, 8) rcm_split_col_kernel(const Sp
             extrap |= (midT < tref + cst.t_pert[0]) | (midT > tref + cst.t_pert[cst.n_tpert - 1]);
             sit[r * C + cc] = it;
             tbi[TBI_IT + r * C + cc] = it;
-            tb[TB_DELT + r * C + cc] = (midT - t0) / (t1 - t0);
+            const double dT = (midT - t0) / (t1 - t0);
+            tb[TB_DELT + r * C + cc] = dT;
+            tb[TB_DTDP + r * C + cc] = __dmul_rn(dT, cst.delP[r]);
         }
     };
     if (f.first) indices();  // tau of the initial profile is built BEFORE the first sort (main.cpp:500-504)
@@ -234,7 +242,7 @@ __global__ void __launch_bounds__(SPLIT_COL_NT, 8) rcm_split_col_kernel(const Sp
     __syncthreads();
     for (int i = tid; i < LC; i += NT) {
         const int r = i / C;
-        tbi[TBI_ROWSEL + i] = (NCAND * r + min(sit[i] - sitmin[r], NCAND - 1)) * ROWB;
+        tbi[TBI_ROWSEL + i] = (NCAND * r + min(sit[i] - sitmin[r], NCAND - 1)) * ROWS3;
     }
     if (tid == 0) {
         // extrapolated cross sections can come out negative: such a tile also takes the global-memory K1, which clamps
@@ -272,10 +280,11 @@ __device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned phase) {
 
 // ------------------------------------------------------------------------------------------
 // K1-K4 for (tile, split) units.  Persistent CTAs (3 per SM, 168 registers), units by atomic counter.
-// Shared memory: exp table 8 KB | four row buffers 4 x 9,600 B (after the wavelength loop: the groups' partial fluxes)
-// | tile block 20,992 B | Planck factors 2 KB | mbarrier, next unit.
+// Shared memory: exp table 8 KB | four row buffers 4 x 7,680 B (after the wavelength loop: the groups' partial fluxes)
+// | tile block 23,552 B | Planck factors 2 KB | mbarrier, next unit.
 // ------------------------------------------------------------------------------------------
-constexpr size_t SPLIT_SMEM = (size_t)EXP_TAB * EXP_REP * 8 + (size_t)SPLIT_G * ROWBUF + TILE_BYTES + 2 * PLK_MAX * 8 + 16;
+constexpr size_t SPLIT_SMEM = (size_t)EXP_TAB * EXP_REP * 8 + (size_t)SPLIT_G * ROWBUF3 + TILE_BYTES + 2 * PLK_MAX * 8 + 16;
+static_assert(SPLIT_PART * 8 <= ROWBUF3, "a warp's row buffer carries its partial fluxes after the wavelength loop");
 
 template <bool CLAMPK>
 __global__ void __launch_bounds__(SPLIT_NT, 3) rcm_split_rt_kernel(const SplitArgs a) {
@@ -283,7 +292,7 @@ __global__ void __launch_bounds__(SPLIT_NT, 3) rcm_split_rt_kernel(const SplitAr
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* const s_exp = reinterpret_cast<double*>(smem_raw);
     unsigned char* const s_rows = smem_raw + (size_t)EXP_TAB * EXP_REP * 8;
-    double* const tb = reinterpret_cast<double*>(s_rows + (size_t)G * ROWBUF);
+    double* const tb = reinterpret_cast<double*>(s_rows + (size_t)G * ROWBUF3);
     const int* const tbi = reinterpret_cast<const int*>(tb + TB_DOUBLES);
     double* const s_plk = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(tb) + TILE_BYTES);
     unsigned long long* const s_mbar = reinterpret_cast<unsigned long long*>(s_plk + 2 * PLK_MAX);
@@ -303,7 +312,7 @@ __global__ void __launch_bounds__(SPLIT_NT, 3) rcm_split_rt_kernel(const SplitAr
         }
     const unsigned mbar = (unsigned)__cvta_generic_to_shared(s_mbar);
     const unsigned tb_addr = (unsigned)__cvta_generic_to_shared(tb);
-    unsigned char* const rows = s_rows + (size_t)warp * ROWBUF;
+    unsigned char* const rows = s_rows + (size_t)warp * ROWBUF3;
     const unsigned rows_addr = (unsigned)__cvta_generic_to_shared(rows);
     if (tid == 0) {
         mbar_init(mbar, 1);
@@ -320,30 +329,39 @@ __global__ void __launch_bounds__(SPLIT_NT, 3) rcm_split_rt_kernel(const SplitAr
 
     auto request_rows = [&](int w) {  // as in the fused kernel: 60 rows of wavelength w, lane q copies rows q and q + 32
         __syncwarp();
-        const char* base = reinterpret_cast<const char*>(a.coef) + (size_t)w * ROWB;
+        const char* base = reinterpret_cast<const char*>(a.coef) + (size_t)w * ROWB3;
         for (int row = lane; row < NCAND * NLAY; row += 32) {
-            const char* src = base + (size_t)tbi[TBI_ROWOFF + row] * ROWB;
-            const unsigned dst = rows_addr + row * ROWB;
+            const char* src = base + (size_t)tbi[TBI_ROWOFF + row] * ROWB3;
+            const unsigned dst = rows_addr + row * ROWS3;
 #pragma unroll
-            for (int part = 0; part < ROWB / 16; ++part) cp_async16(dst + part * 16, src + part * 16);
+            for (int part = 0; part < ROWB3 / 16; ++part) cp_async16(dst + part * 16, src + part * 16);
         }
         cp_async_commit();
     };
-    // K1 for owned layer j from the coefficients at cf (repwvl_thermal.cpp:235-246, the reference's operation order)
+    // K1 for owned layer j from the row at cf: the bilinear (p, T) interpolation of repwvl_thermal.cpp:235-246,
+    //   x = c0 + cT*dT + cP*dP + cPT*dT*dP,   tau = numDens * sum_k x_k * vmr_k,
+    // contracted to three FMAs per species on {c0 + cP*dP, cT, cPT} and dT, dT*dP (17 instead of 42 FP64 instructions per
+    // layer and wavelength; within a few ulp of the reference's operation order - the bit-exact form is rcm_build_tau's).
+    // Staged and global-memory variant evaluate the same expression on the same numbers: bit-identical.
     auto tau_from = [&](int j, const double2* cf, double cl) -> double {
         const int r = h * HALF + j;
-        const double dT = tb[TB_DELT + sb + j * C], dP = cst.delP[r];
+        const double dT = tb[TB_DELT + sb + j * C], dTdP = tb[TB_DTDP + sb + j * C];
+        double c[16];
+#pragma unroll
+        for (int q2 = 0; q2 < 8; ++q2) {
+            const double2 v = cf[q2];
+            c[2 * q2] = v.x;
+            c[2 * q2 + 1] = v.y;
+        }
         double acc = 0.0;
 #pragma unroll
         for (int k = 0; k < NACT; ++k) {
-            const double2 c0T = cf[2 * k], cPPT = cf[2 * k + 1];
-            double v = __dadd_rn(c0T.x, __dmul_rn(c0T.y, dT));
-            v = __dadd_rn(v, cPPT.x);
-            v = __dadd_rn(v, __dmul_rn(__dmul_rn(cPPT.y, dT), dP));
-            acc = __dadd_rn(acc, __dmul_rn(v, tb[TB_VMR + k * NLAY * C + sb + j * C]));
+            double v = fma(c[3 * k + 1], dT, c[3 * k]);
+            v = fma(c[3 * k + 2], dTdP, v);
+            acc = fma(v, tb[TB_VMR + k * NLAY * C + sb + j * C], acc);
         }
-        acc = __dmul_rn(acc, cst.numDens[r]);
-        if (cst.cloud_row == r) acc = __dadd_rn(acc, cl);  // main.cpp:270
+        acc = acc * cst.numDens[r];
+        if (cst.cloud_row == r) acc = acc + cl;  // main.cpp:270
         return acc;
     };
 
@@ -377,7 +395,7 @@ __global__ void __launch_bounds__(SPLIT_NT, 3) rcm_split_rt_kernel(const SplitAr
 #pragma unroll
                 for (int j = 0; j < HALF; ++j) {
                     const int cell = cst.ipcell[h * HALF + j] + tbi[TBI_IT + sb + j * C];
-                    const double v = tau_from(j, reinterpret_cast<const double2*>(a.coef) + (size_t)(cell * nwvl + w) * 2 * NACT, cl);
+                    const double v = tau_from(j, reinterpret_cast<const double2*>(a.coef) + (size_t)(cell * nwvl + w) * 8, cl);
                     tau[j] = fmax(CLAMPK ? v : fmin(v, a.tau_clamp), TAU_FLOOR);
                 }
             }
@@ -392,7 +410,7 @@ __global__ void __launch_bounds__(SPLIT_NT, 3) rcm_split_rt_kernel(const SplitAr
         }
         // ---- K4: the four groups' partial fluxes through the row buffers, summed in group order -------------------
         {
-            double* part = reinterpret_cast<double*>(s_rows + (size_t)g * ROWBUF);
+            double* part = reinterpret_cast<double*>(s_rows + (size_t)g * ROWBUF3);
 #pragma unroll
             for (int j = 0; j < HALF; ++j) {
                 const int l = h ? (NLAY - 1 - j) : j;
@@ -414,7 +432,7 @@ __global__ void __launch_bounds__(SPLIT_NT, 3) rcm_split_rt_kernel(const SplitAr
             double sum = 0.0;
             if (i / C != NLAY) {
 #pragma unroll
-                for (int gg = 0; gg < G; ++gg) sum += reinterpret_cast<const double*>(s_rows + (size_t)gg * ROWBUF)[i];
+                for (int gg = 0; gg < G; ++gg) sum += reinterpret_cast<const double*>(s_rows + (size_t)gg * ROWBUF3)[i];
             }
             out[i] = sum;
         }
