@@ -327,14 +327,18 @@ __global__ void __launch_bounds__(SPLIT_NT, 3) rcm_split_rt_kernel(const SplitAr
     // s_next[1]: units this CTA has taken from the counter (a.quota: it leaves its slot to waiting kernels after that many);
     // kept in shared memory - thread 0 alone needs it, once per unit, and the kernel has no register to spare
 
-    auto request_rows = [&](int w) {  // as in the fused kernel: 60 rows of wavelength w, lane q copies rows q and q + 32
+    // The 60 rows of wavelength w (three candidates per layer, 128 bytes each) into this warp's buffer: eight consecutive
+    // lanes copy the eight 16-byte pieces of one row, four rows per instruction - contiguous 128 bytes on the global side
+    // (4 x 4 sectors per LDGSTS instead of 32 lanes in 32 rows) and conflict-free on the shared side (with a lane per row the
+    // copies took 30 shared-memory wavefronts per instruction instead of 4: a third of the kernel's shared-memory traffic).
+    auto request_rows = [&](int w) {
         __syncwarp();
-        const char* base = reinterpret_cast<const char*>(a.coef) + (size_t)w * ROWB3;
-        for (int row = lane; row < NCAND * NLAY; row += 32) {
-            const char* src = base + (size_t)tbi[TBI_ROWOFF + row] * ROWB3;
-            const unsigned dst = rows_addr + row * ROWS3;
+        const char* base = reinterpret_cast<const char*>(a.coef) + (size_t)w * ROWB3 + (lane & 7) * 16;
+        const unsigned dst0 = rows_addr + (lane & 7) * 16;
 #pragma unroll
-            for (int part = 0; part < ROWB3 / 16; ++part) cp_async16(dst + part * 16, src + part * 16);
+        for (int i = 0; i < NCAND * NLAY / 4; ++i) {
+            const int row = (lane >> 3) + 4 * i;
+            cp_async16(dst0 + row * ROWS3, base + (size_t)tbi[TBI_ROWOFF + row] * ROWB3);
         }
         cp_async_commit();
     };
