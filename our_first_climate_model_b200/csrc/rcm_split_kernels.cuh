@@ -28,16 +28,22 @@ constexpr int SPLIT_IPU = 5;  // wavelength rounds (of SPLIT_G wavelengths) per 
 constexpr int SPLIT_COL_NT = 128;  // K5 kernel: 8 CTAs (tiles) per SM at 64 registers
 
 // the tile block (doubles, then ints); per-layer rows in pair order r = prow(l)
+// A [20][16] array of the block keeps its rows 10..19 - the ones the h = 1 lanes read - half a bank row further on (8 doubles
+// resp. 16 ints of padding after row 9): the two lanes of a pair read rows j and 10 + j of the same column in the same
+// instruction, and at a distance of exactly 10 rows (1280 bytes) they would hit the same bank every time.
+constexpr int TBD_LEN = NLAY * SPLIT_C + 8, TBI_LEN = NLAY * SPLIT_C + 16;
+__host__ __device__ constexpr int tbd(int r, int cc) { return r * SPLIT_C + cc + (r >= HALF ? 8 : 0); }   // doubles
+__host__ __device__ constexpr int tbix(int r, int cc) { return r * SPLIT_C + cc + (r >= HALF ? 16 : 0); }  // ints
 constexpr int TB_INVT = 0;                               // [20][16]  EXP_L2E / T (sorted profile): Planck exponent factor
-constexpr int TB_DELT = TB_INVT + NLAY * SPLIT_C;        // [20][16]  interpolation weight in T
-constexpr int TB_DTDP = TB_DELT + NLAY * SPLIT_C;        // [20][16]  that weight times the layer's weight in p (rounded once)
-constexpr int TB_VMR = TB_DTDP + NLAY * SPLIT_C;         // [5][20][16]
-constexpr int TB_INVTS = TB_VMR + 5 * NLAY * SPLIT_C;    // [16]      EXP_L2E / T_surface
+constexpr int TB_DELT = TB_INVT + TBD_LEN;               // [20][16]  interpolation weight in T
+constexpr int TB_DTDP = TB_DELT + TBD_LEN;               // [20][16]  that weight times the layer's weight in p (rounded once)
+constexpr int TB_VMR = TB_DTDP + TBD_LEN;                // [5][20][16]
+constexpr int TB_INVTS = TB_VMR + 5 * TBD_LEN;           // [16]      EXP_L2E / T_surface
 constexpr int TB_CLOUD = TB_INVTS + SPLIT_C;             // [16]
 constexpr int TB_DOUBLES = TB_CLOUD + SPLIT_C;
 constexpr int TBI_IT = 0;                                // [20][16]  temperature interval (LowerPos)
-constexpr int TBI_ROWSEL = TBI_IT + NLAY * SPLIT_C;      // [20][16]  byte offset of the (layer, column)'s row in a warp's row buffer
-constexpr int TBI_ROWOFF = TBI_ROWSEL + NLAY * SPLIT_C;  // [20][NCAND] first table row of every candidate
+constexpr int TBI_ROWSEL = TBI_IT + TBI_LEN;             // [20][16]  byte offset of the (layer, column)'s row in a warp's row buffer
+constexpr int TBI_ROWOFF = TBI_ROWSEL + TBI_LEN;         // [20][NCAND] first table row of every candidate
 constexpr int TBI_OUTSIDE = TBI_ROWOFF + NLAY * NCAND;   // some column needs a row beyond the candidates: global-memory K1
 constexpr int TB_INTS = (TBI_OUTSIDE + 1 + 3) / 4 * 4;
 constexpr int TILE_BYTES = TB_DOUBLES * 8 + TB_INTS * 4;
@@ -164,10 +170,10 @@ __global__ void __launch_bounds__(SPLIT_COL_NT, 8) rcm_split_col_kernel(const Sp
             const double t0 = tref + cst.t_pert[it], t1 = tref + cst.t_pert[it + 1];
             extrap |= (midT < tref + cst.t_pert[0]) | (midT > tref + cst.t_pert[cst.n_tpert - 1]);
             sit[r * C + cc] = it;
-            tbi[TBI_IT + r * C + cc] = it;
+            tbi[TBI_IT + tbix(r, cc)] = it;
             const double dT = (midT - t0) / (t1 - t0);
-            tb[TB_DELT + r * C + cc] = dT;
-            tb[TB_DTDP + r * C + cc] = __dmul_rn(dT, cst.delP[r]);
+            tb[TB_DELT + tbd(r, cc)] = dT;
+            tb[TB_DTDP + tbd(r, cc)] = __dmul_rn(dT, cst.delP[r]);
         }
     };
     if (f.first) indices();  // tau of the initial profile is built BEFORE the first sort (main.cpp:500-504)
@@ -218,11 +224,11 @@ __global__ void __launch_bounds__(SPLIT_COL_NT, 8) rcm_split_col_kernel(const Sp
                 v = a.vmr[gi];
             }
         }
-        tb[TB_VMR + (sp * NLAY + prow(l)) * C + cc] = v;
+        tb[TB_VMR + sp * TBD_LEN + tbd(prow(l), cc)] = v;
     }
     if (!f.first) indices();
     // (T_floor: a column colder than ~5 K would take the fast exp's exponent out of range - its source is 0 either way)
-    for (int i = tid; i < LC; i += NT) tb[TB_INVT + prow(i / C) * C + i % C] = (1.0 / fmax(sT[i], a.T_floor)) * L2E64;
+    for (int i = tid; i < LC; i += NT) tb[TB_INVT + tbd(prow(i / C), i % C)] = (1.0 / fmax(sT[i], a.T_floor)) * L2E64;
     if (tid < C) {
         tb[TB_INVTS + tid] = (1.0 / fmax(sTs[tid], a.T_floor)) * L2E64;
         tb[TB_CLOUD + tid] = a.cloud_col ? a.cloud_col[col0 + (tid < ncl ? tid : 0)] : cst.cloud_tau;
@@ -242,7 +248,7 @@ __global__ void __launch_bounds__(SPLIT_COL_NT, 8) rcm_split_col_kernel(const Sp
     __syncthreads();
     for (int i = tid; i < LC; i += NT) {
         const int r = i / C;
-        tbi[TBI_ROWSEL + i] = (NCAND * r + min(sit[i] - sitmin[r], NCAND - 1)) * ROWS3;
+        tbi[TBI_ROWSEL + tbix(r, i % C)] = (NCAND * r + min(sit[i] - sitmin[r], NCAND - 1)) * ROWS3;
     }
     if (tid == 0) {
         // extrapolated cross sections can come out negative: such a tile also takes the global-memory K1, which clamps
@@ -300,7 +306,7 @@ __global__ void __launch_bounds__(SPLIT_NT, 3) rcm_split_rt_kernel(const SplitAr
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int h = tid & 1, q = tid >> 1, c = q % C, g = q / C;  // g == warp: one warp per wavelength group
-    const int sb = h * HALF * C + c;
+    const int sb = tbd(h * HALF, c), sbi = tbix(h * HALF, c);  // this thread's first row in the block's double / int arrays
     const int nwvl = cst.nwvl;
     for (int i = tid; i < EXP_TAB * EXP_REP; i += NT) s_exp[i] = a.exp_tab[i / EXP_REP];
     const unsigned tab_lane = (unsigned)__cvta_generic_to_shared(s_exp + (lane & (EXP_REP - 1)));
@@ -362,7 +368,7 @@ __global__ void __launch_bounds__(SPLIT_NT, 3) rcm_split_rt_kernel(const SplitAr
         for (int k = 0; k < NACT; ++k) {
             double v = fma(c[3 * k + 1], dT, c[3 * k]);
             v = fma(c[3 * k + 2], dTdP, v);
-            acc = fma(v, tb[TB_VMR + k * NLAY * C + sb + j * C], acc);
+            acc = fma(v, tb[TB_VMR + k * TBD_LEN + sb + j * C], acc);
         }
         acc = acc * cst.numDens[r];
         if (cst.cloud_row == r) acc = acc + cl;  // main.cpp:270
@@ -391,14 +397,14 @@ __global__ void __launch_bounds__(SPLIT_NT, 3) rcm_split_rt_kernel(const SplitAr
                 __syncwarp();
 #pragma unroll
                 for (int j = 0; j < HALF; ++j) {
-                    const double v = tau_from(j, reinterpret_cast<const double2*>(rows + tbi[TBI_ROWSEL + sb + j * C]), cl);
+                    const double v = tau_from(j, reinterpret_cast<const double2*>(rows + tbi[TBI_ROWSEL + sbi + j * C]), cl);
                     tau[j] = CLAMPK ? v : fmin(v, a.tau_clamp);
                 }
                 if (item + 1 < item1) request_rows(min(w_any + G, nwvl - 1));
             } else {
 #pragma unroll
                 for (int j = 0; j < HALF; ++j) {
-                    const int cell = cst.ipcell[h * HALF + j] + tbi[TBI_IT + sb + j * C];
+                    const int cell = cst.ipcell[h * HALF + j] + tbi[TBI_IT + sbi + j * C];
                     const double v = tau_from(j, reinterpret_cast<const double2*>(a.coef) + (size_t)(cell * nwvl + w) * 8, cl);
                     tau[j] = fmax(CLAMPK ? v : fmin(v, a.tau_clamp), TAU_FLOOR);
                 }
