@@ -966,12 +966,19 @@ int rcm_set_lbl_tables(rcm_solver* s, const double* wvl, const double* tau5, int
     const size_t n = (size_t)nwvl;
     CU(dalloc(s->d_lbl_lo, n));
     CU(dalloc(s->d_lbl_hi, n));
-    CU(dalloc(s->d_lbl_tau5, 5 * n * NLAY));
+    CU(dalloc(s->d_lbl_tau5, 3 * n * NLAY));
     CU(dalloc(s->d_lbl_h2o_ref, (size_t)NLAY));
     CU(dalloc(s->d_lbl_o3_ref, (size_t)NLAY));
     CU(cudaMemcpy(s->d_lbl_lo, lo.data(), n * sizeof(double), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(s->d_lbl_hi, hi.data(), n * sizeof(double), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(s->d_lbl_tau5, tau5, 5 * n * NLAY * sizeof(double), cudaMemcpyHostToDevice));
+    {   // device planes: tau_H2O, tau_O3, and the column-independent part f_CO2 * tau_CO2 + tau_CH4 + tau_N2O
+        const size_t plane = n * NLAY;
+        std::vector<double> t3(3 * plane);
+        std::memcpy(&t3[0], tau5, plane * sizeof(double));
+        std::memcpy(&t3[plane], tau5 + 2 * plane, plane * sizeof(double));
+        for (size_t i = 0; i < plane; ++i) t3[2 * plane + i] = co2_factor * tau5[plane + i] + tau5[3 * plane + i] + tau5[4 * plane + i];
+        CU(cudaMemcpy(s->d_lbl_tau5, t3.data(), t3.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
     CU(cudaMemcpy(s->d_lbl_h2o_ref, h2o_ref, NLAY * sizeof(double), cudaMemcpyHostToDevice));
     s->lbl_has_o3_ref = o3_ref != nullptr;
     if (o3_ref) CU(cudaMemcpy(s->d_lbl_o3_ref, o3_ref, NLAY * sizeof(double), cudaMemcpyHostToDevice));
@@ -1180,7 +1187,7 @@ static int lbl_advance(rcm_solver* s, int nsteps) {
     a.tau_clamp = s->tau_clamp;
     a.wvl_lo = s->d_lbl_lo;
     a.wvl_hi = s->d_lbl_hi;
-    a.tau5 = s->d_lbl_tau5;
+    a.tau3 = s->d_lbl_tau5;
     a.h2o_ref = s->d_lbl_h2o_ref;
     a.o3_ref = s->lbl_has_o3_ref ? s->d_lbl_o3_ref : nullptr;
     a.exp_tab = s->d_exp_tab;

@@ -354,7 +354,7 @@ cudaError_t rcm_launch_cplkavg(int n, const double* lo, const double* hi, const 
 }
 
 size_t rcm_lbl_smem_bytes(int C, int nthreads) {
-    return ((size_t)EXP_TAB * EXP_REP + (size_t)NLAY * C * 3 + 2 * C + (size_t)HALF * nthreads +
+    return ((size_t)EXP_TAB * EXP_REP + (size_t)TBD_LEN * 3 + 2 * C + (size_t)HALF * nthreads +
             (size_t)NLEV * (nthreads / 2)) * sizeof(double);
 }
 

@@ -114,7 +114,7 @@ struct LblArgs {
     double co2_factor, tau_clamp;
     const double* __restrict__ wvl_lo;   // [nwvl] bin edges, nm
     const double* __restrict__ wvl_hi;
-    const double* __restrict__ tau5;     // [5][nwvl][20]  H2O, CO2, O3, CH4, N2O
+    const double* __restrict__ tau3;     // [3][nwvl][20]  H2O, O3, and f_CO2 * CO2 + CH4 + N2O (the column-independent part)
     const double* __restrict__ h2o_ref;  // [20]
     const double* __restrict__ o3_ref;   // [20] or NULL
     const double* __restrict__ exp_tab;

@@ -154,22 +154,23 @@ __global__ void __launch_bounds__(NT, 384 / NT) rcm_lbl_rt_kernel(const LblArgs 
     constexpr int G = NT / (2 * C), GC = G * C;
     double* p = reinterpret_cast<double*>(smem_raw);
     double* s_tab = p; p += EXP_TAB * EXP_REP;
-    double* s_T = p;   p += NLAY * C;
-    double* s_sH = p;  p += NLAY * C;
-    double* s_sO = p;  p += NLAY * C;
+    static_assert(C == 16, "tbd() is laid out for 16-column tiles");
+    double* s_T = p;   p += TBD_LEN;  // [20][C] in pair order, rows 10..19 half a bank row further on (tbd)
+    double* s_sH = p;  p += TBD_LEN;
+    double* s_sO = p;  p += TBD_LEN;
     double* s_Ts = p;  p += C;
     double* s_cl = p;  p += C;
     double* s_B = p;   p += HALF * NT;  // [10][NT] Planck source of the thread's ten layers (written by a rolled loop)
     double* s_Ep = p;  // [21][GC]
     const int tid = threadIdx.x, lane = tid & 31;
     const int h = tid & 1, q = tid >> 1, c = q % C, g = q / C;
-    const int sb = h * HALF * C + c;
+    const int sb = tbd(h * HALF, c);
     for (int i = tid; i < EXP_TAB * EXP_REP; i += NT) s_tab[i] = a.exp_tab[i / EXP_REP];
     const unsigned tab_lane = (unsigned)__cvta_generic_to_shared(s_tab + (lane & (EXP_REP - 1)));
     const int tile = blockIdx.x % a.ntiles, chunk = blockIdx.x / a.ntiles;
     const int col0 = tile * C, ncl = min(C, a.ncol - col0);
     for (int i = tid; i < NLAY * C; i += NT) {
-        const int l = i / C, cc = i % C, r = prow(l) * C + cc;
+        const int l = i / C, cc = i % C, r = tbd(prow(l), cc);
         const bool ok = cc < ncl;
         const size_t gi = (size_t)(col0 + cc) * NLAY + l;
         s_T[r] = ok ? a.Tlayer[gi] : 250.0;
@@ -197,16 +198,14 @@ __global__ void __launch_bounds__(NT, 384 / NT) rcm_lbl_rt_kernel(const LblArgs 
         double tau[HALF], Bo[HALF];
         const double lo = __ldg(a.wvl_lo + w), hi = __ldg(a.wvl_hi + w);
         const double whi = 1.0E7 / lo, wlo = 1.0E7 / hi;  // cplkavg.cpp:141-142, once per wavelength
-        const double* t5 = a.tau5 + (size_t)w * NLAY;
+        // tau = tau_H2O * s_H2O + tau_O3 * s_O3 + (f_CO2 * tau_CO2 + tau_CH4 + tau_N2O): the bracket does not depend on the
+        // column and is summed once when the tables are uploaded (rcm_set_lbl_tables); two FMAs per layer and wavelength
+        const double* t3 = a.tau3 + (size_t)w * NLAY;
 #pragma unroll
         for (int j = 0; j < HALF; ++j) {
             const int l = h ? (NLAY - 1 - j) : j;
-            double v = __dmul_rn(__ldg(t5 + l), s_sH[sb + j * C]);
-            v = __dadd_rn(v, __dmul_rn(a.co2_factor, __ldg(t5 + plane + l)));
-            v = __dadd_rn(v, __dmul_rn(__ldg(t5 + 2 * plane + l), s_sO[sb + j * C]));
-            v = __dadd_rn(v, __ldg(t5 + 3 * plane + l));
-            v = __dadd_rn(v, __ldg(t5 + 4 * plane + l));
-            if (cst.cloud_row == h * HALF + j) v = __dadd_rn(v, s_cl[c]);
+            double v = fma(__ldg(t3 + l), s_sH[sb + j * C], fma(__ldg(t3 + plane + l), s_sO[sb + j * C], __ldg(t3 + 2 * plane + l)));
+            if (cst.cloud_row == h * HALF + j) v = v + s_cl[c];
             tau[j] = CLAMPK ? v : fmin(v, a.tau_clamp);
         }
         // The band-integrated Planck function of the ten layers in a ROLLED loop through shared memory: inlined ten

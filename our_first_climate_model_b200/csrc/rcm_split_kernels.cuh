@@ -31,9 +31,7 @@ constexpr int SPLIT_COL_NT = 128;  // K5 kernel: 8 CTAs (tiles) per SM at 64 reg
 // A [20][16] array of the block keeps its rows 10..19 - the ones the h = 1 lanes read - half a bank row further on (8 doubles
 // resp. 16 ints of padding after row 9): the two lanes of a pair read rows j and 10 + j of the same column in the same
 // instruction, and at a distance of exactly 10 rows (1280 bytes) they would hit the same bank every time.
-constexpr int TBD_LEN = NLAY * SPLIT_C + 8, TBI_LEN = NLAY * SPLIT_C + 16;
-__host__ __device__ constexpr int tbd(int r, int cc) { return r * SPLIT_C + cc + (r >= HALF ? 8 : 0); }   // doubles
-__host__ __device__ constexpr int tbix(int r, int cc) { return r * SPLIT_C + cc + (r >= HALF ? 16 : 0); }  // ints
+// (tbd / tbix / TBD_LEN / TBI_LEN: rcm_step_kernel.cuh, shared with the LBL kernel)
 constexpr int TB_INVT = 0;                               // [20][16]  EXP_L2E / T (sorted profile): Planck exponent factor
 constexpr int TB_DELT = TB_INVT + TBD_LEN;               // [20][16]  interpolation weight in T
 constexpr int TB_DTDP = TB_DELT + TBD_LEN;               // [20][16]  that weight times the layer's weight in p (rounded once)

@@ -132,6 +132,12 @@ __device__ __forceinline__ void sweep_item(const double (&tau)[HALF], const doub
 // top-down, lane h=1 owns layers 19..10 (bottom-up), both as local index j=0..9.  Per-layer
 // arrays are stored in this order: row(l) = l for l<10, 29-l otherwise (= 10*h + j).
 __device__ __forceinline__ constexpr int prow(int l) { return l < HALF ? l : 29 - l; }
+// [20][16] shared-memory arrays read by (column c, half h) lanes at rows j and 10 + j in the same instruction keep their
+// rows 10..19 half a bank row further on (8 doubles resp. 16 ints of padding after row 9): at a distance of exactly 10 rows
+// (1280 bytes) the two lanes of a pair would hit the same bank every time.
+constexpr int TBD_LEN = NLAY * 16 + 8, TBI_LEN = NLAY * 16 + 16;
+__host__ __device__ constexpr int tbd(int r, int cc) { return r * 16 + cc + (r >= HALF ? 8 : 0); }    // doubles
+__host__ __device__ constexpr int tbix(int r, int cc) { return r * 16 + cc + (r >= HALF ? 16 : 0); }  // ints
 
 constexpr double TAU_FLOOR = -8.0;       // lower clamp of tau in front of the transmissions: exp(8 * 60) is still in range
 constexpr int ROWB = 5 * 32;             // bytes of one table row: 5 active species x {c0, cT, cP, cPT}
