@@ -241,7 +241,8 @@ __global__ void __launch_bounds__(SPLIT_COL_NT, 8) rcm_split_col_kernel(const Sp
         }
         sitmin[tid] = mn;
         sout[tid] = (mx - mn >= NCAND);
-        for (int k = 0; k < NCAND; ++k) tbi[TBI_ROWOFF + NCAND * tid + k] = (cst.ipcell[tid] + min(mn + k, cst.n_tpert - 2)) * nwvl;
+        // (byte offset of the candidate's first row in the table: 32 bits are plenty - 20 layers x 8 intervals x nwvl x 128 B)
+        for (int k = 0; k < NCAND; ++k) tbi[TBI_ROWOFF + NCAND * tid + k] = (cst.ipcell[tid] + min(mn + k, cst.n_tpert - 2)) * nwvl * ROWB3;
     }
     __syncthreads();
     for (int i = tid; i < LC; i += NT) {
@@ -338,12 +339,13 @@ __global__ void __launch_bounds__(SPLIT_NT, 3) rcm_split_rt_kernel(const SplitAr
     auto request_rows = [&](int w) {
         __syncwarp();
         const char* base = reinterpret_cast<const char*>(a.coef) + (size_t)w * ROWB3 + (lane & 7) * 16;
-        const unsigned dst0 = rows_addr + (lane & 7) * 16;
+        const unsigned dst0 = rows_addr + (lane & 7) * 16 + (lane >> 3) * ROWS3;
+        const int* ro = tbi + TBI_ROWOFF + (lane >> 3);
+        unsigned off[NCAND * NLAY / 4];  // the 15 row offsets first, then the 15 copies back to back
 #pragma unroll
-        for (int i = 0; i < NCAND * NLAY / 4; ++i) {
-            const int row = (lane >> 3) + 4 * i;
-            cp_async16(dst0 + row * ROWS3, base + (size_t)tbi[TBI_ROWOFF + row] * ROWB3);
-        }
+        for (int i = 0; i < NCAND * NLAY / 4; ++i) off[i] = (unsigned)ro[4 * i];
+#pragma unroll
+        for (int i = 0; i < NCAND * NLAY / 4; ++i) cp_async16(dst0 + 4 * i * ROWS3, base + off[i]);
         cp_async_commit();
     };
     // K1 for owned layer j from the row at cf: the bilinear (p, T) interpolation of repwvl_thermal.cpp:235-246,
