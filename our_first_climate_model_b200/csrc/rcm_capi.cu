@@ -271,6 +271,7 @@ int refresh_const(rcm_solver* s) {
     d.cloud_layer = s->p.cloud_layer;
     d.cloud_row = s->p.cloud_layer < 0 ? -1 : (s->p.cloud_layer < HALF ? s->p.cloud_layer : 29 - s->p.cloud_layer);
     d.cloud_tau = s->p.cloud_tau;
+    for (int r = 0; r < RCM_NLAYER; ++r) d.cloud_w[r] = (r == d.cloud_row) ? 1.0 : 0.0;
     d.dp = s->p.dp;
     d.max_dT = s->p.max_dT;
     d.dt_cap = s->p.dt_cap;

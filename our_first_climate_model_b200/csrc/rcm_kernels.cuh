@@ -43,6 +43,7 @@ struct DevConst {
     int ip[NLAY];
     int ipcell[NLAY];  // row * (n_tpert-1): first cell of the layer's block in the per-layer coefficient table
     int cloud_row;     // pair-order row of the cloud layer, -1 if none
+    double cloud_w[NLAY];  // 1.0 on that row, 0.0 elsewhere: tau += cloud_w[r] * cloud_tau as one FMA (exact either way)
     double delP[NLAY], numDens[NLAY], tref_ip[NLAY], player[NLAY], conv[NLAY];
     double t_pert[MAX_TPERT];
     // Angle schedule.  The quadrature nodes are visited in chains mu, mu/3, mu/9, ...: the head of a chain

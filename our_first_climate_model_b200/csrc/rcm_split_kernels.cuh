@@ -371,10 +371,14 @@ __global__ void __launch_bounds__(SPLIT_NT, 3) rcm_split_rt_kernel(const SplitAr
             acc = fma(v, tb[TB_VMR + k * TBD_LEN + sb + j * C], acc);
         }
         acc = acc * cst.numDens[r];
-        if (cst.cloud_row == r) acc = acc + cl;  // main.cpp:270
-        return acc;
+        return fma(cst.cloud_w[r], cl, acc);  // main.cpp:270: + cl on the cloud layer, + 0 * cl (exact) elsewhere
     };
 
+    // Upper clamp of tau in front of the transmissions (exp(-tau_clamp / mu) ~ 1e-100 for every mu) as ONE integer minimum
+    // on the high word - for non-negative doubles the order of the high words is the order of the numbers, negative ones
+    // stay as they are - instead of DSETP + two FSEL: the result may exceed tau_clamp by less than 2^-20 of it, irrelevant here.
+    const int tau_clamp_hi = __double2hiint(a.tau_clamp);
+    auto clamp_hi = [](double v, int hi_max) { return __hiloint2double(min(__double2hiint(v), hi_max), __double2loint(v)); };
     while (unit < a.nunits) {
         const int tile = unit / a.nsplit, split = unit - tile * a.nsplit;
         mbar_wait(mbar, phase);  // the tile block of this unit has landed
@@ -398,7 +402,7 @@ __global__ void __launch_bounds__(SPLIT_NT, 3) rcm_split_rt_kernel(const SplitAr
 #pragma unroll
                 for (int j = 0; j < HALF; ++j) {
                     const double v = tau_from(j, reinterpret_cast<const double2*>(rows + tbi[TBI_ROWSEL + sbi + j * C]), cl);
-                    tau[j] = CLAMPK ? v : fmin(v, a.tau_clamp);
+                    tau[j] = CLAMPK ? v : clamp_hi(v, tau_clamp_hi);
                 }
                 if (item + 1 < item1) request_rows(min(w_any + G, nwvl - 1));
             } else {
@@ -406,7 +410,7 @@ __global__ void __launch_bounds__(SPLIT_NT, 3) rcm_split_rt_kernel(const SplitAr
                 for (int j = 0; j < HALF; ++j) {
                     const int cell = cst.ipcell[h * HALF + j] + tbi[TBI_IT + sbi + j * C];
                     const double v = tau_from(j, reinterpret_cast<const double2*>(a.coef) + (size_t)(cell * nwvl + w) * 8, cl);
-                    tau[j] = fmax(CLAMPK ? v : fmin(v, a.tau_clamp), TAU_FLOOR);
+                    tau[j] = fmax(CLAMPK ? v : clamp_hi(v, tau_clamp_hi), TAU_FLOOR);
                 }
             }
             // K2: Planck source B = k_w / (exp(c_w / T) - 1) (main.cpp:188-191, wavelength-only factors from the host)
