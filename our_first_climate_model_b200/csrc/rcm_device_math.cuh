@@ -59,6 +59,13 @@ __device__ __forceinline__ double div_fast(double a, double d) {
     return fma(fma(-d, q, a), r, q);
 }
 
+// Upper clamp of a tau in front of the transmissions (exp(-tau_clamp / mu) ~ 1e-100 for every mu) as ONE integer minimum on
+// the high word - for non-negative doubles the order of the high words is the order of the numbers, negative ones stay as
+// they are - instead of DSETP + two FSEL; the result may exceed the clamp by less than 2^-20 of it, irrelevant here.
+__device__ __forceinline__ double clamp_hi(double v, int hi_max) {
+    return __hiloint2double(min(__double2hiint(v), hi_max), __double2loint(v));
+}
+
 // descending compare-exchange
 __device__ __forceinline__ void cex(double& a, double& b) {
     const double hi = fmax(a, b), lo = fmin(a, b);

@@ -189,6 +189,7 @@ __global__ void __launch_bounds__(NT, 384 / NT) rcm_lbl_rt_kernel(const LblArgs 
     // chunk_len is a multiple of G: every thread runs chunk_len / G items (uniform trip count, see the step
     // kernel); items beyond the last wavelength repeat it with a zero source.
     const int w_lo = chunk * a.chunk_len;
+    const int tau_clamp_hi = __double2hiint(a.tau_clamp);
     const size_t plane = (size_t)a.nwvl * NLAY;
 #pragma unroll 1
     for (int item = 0; item < a.chunk_len / G; ++item) {
@@ -205,8 +206,8 @@ __global__ void __launch_bounds__(NT, 384 / NT) rcm_lbl_rt_kernel(const LblArgs 
         for (int j = 0; j < HALF; ++j) {
             const int l = h ? (NLAY - 1 - j) : j;
             double v = fma(__ldg(t3 + l), s_sH[sb + j * C], fma(__ldg(t3 + plane + l), s_sO[sb + j * C], __ldg(t3 + 2 * plane + l)));
-            if (cst.cloud_row == h * HALF + j) v = v + s_cl[c];
-            tau[j] = CLAMPK ? v : fmin(v, a.tau_clamp);
+            v = fma(cst.cloud_w[h * HALF + j], s_cl[c], v);  // + cloud tau on the cloud layer, + 0 (exact) elsewhere
+            tau[j] = CLAMPK ? v : clamp_hi(v, tau_clamp_hi);
         }
         // The band-integrated Planck function of the ten layers in a ROLLED loop through shared memory: inlined ten
         // times it made the kernel 9,900 instructions long and instruction fetch 6 % of its stalls.

@@ -374,11 +374,7 @@ __global__ void __launch_bounds__(SPLIT_NT, 3) rcm_split_rt_kernel(const SplitAr
         return fma(cst.cloud_w[r], cl, acc);  // main.cpp:270: + cl on the cloud layer, + 0 * cl (exact) elsewhere
     };
 
-    // Upper clamp of tau in front of the transmissions (exp(-tau_clamp / mu) ~ 1e-100 for every mu) as ONE integer minimum
-    // on the high word - for non-negative doubles the order of the high words is the order of the numbers, negative ones
-    // stay as they are - instead of DSETP + two FSEL: the result may exceed tau_clamp by less than 2^-20 of it, irrelevant here.
-    const int tau_clamp_hi = __double2hiint(a.tau_clamp);
-    auto clamp_hi = [](double v, int hi_max) { return __hiloint2double(min(__double2hiint(v), hi_max), __double2loint(v)); };
+    const int tau_clamp_hi = __double2hiint(a.tau_clamp);  // clamp_hi: rcm_device_math.cuh
     while (unit < a.nunits) {
         const int tile = unit / a.nsplit, split = unit - tile * a.nsplit;
         mbar_wait(mbar, phase);  // the tile block of this unit has landed
