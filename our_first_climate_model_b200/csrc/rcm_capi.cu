@@ -965,12 +965,24 @@ int rcm_set_lbl_tables(rcm_solver* s, const double* wvl, const double* tau5, int
         hi[i] = wvl[i] + dh / 2.0;
     }
     const size_t n = (size_t)nwvl;
-    CU(dalloc(s->d_lbl_lo, n));
+    CU(dalloc(s->d_lbl_lo, 4 * n));  // planes: lo, (hi in d_lbl_hi), whi, wlo, and the narrow-band flags as ints
     CU(dalloc(s->d_lbl_hi, n));
     CU(dalloc(s->d_lbl_tau5, 3 * n * NLAY));
     CU(dalloc(s->d_lbl_h2o_ref, (size_t)NLAY));
     CU(dalloc(s->d_lbl_o3_ref, (size_t)NLAY));
     CU(cudaMemcpy(s->d_lbl_lo, lo.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+    {   // per-bin quantities of cplkavg (cplkavg.cpp:141-142, :155), evaluated here once with the reference's expressions
+        std::vector<double> wn(2 * n);
+        std::vector<int> ok(2 * n, 0);  // (ints in a plane of doubles: 2n ints)
+        for (size_t i = 0; i < n; ++i) {
+            const double whi = 1.0E7 / lo[i], wlo = 1.0E7 / hi[i];
+            wn[i] = whi;
+            wn[n + i] = wlo;
+            ok[i] = (whi > wlo && wlo >= 0. && (whi - wlo) / whi < 1.e-2) ? 1 : 0;
+        }
+        CU(cudaMemcpy(s->d_lbl_lo + n, wn.data(), 2 * n * sizeof(double), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(s->d_lbl_lo + 3 * n, ok.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+    }
     CU(cudaMemcpy(s->d_lbl_hi, hi.data(), n * sizeof(double), cudaMemcpyHostToDevice));
     {   // device planes: tau_H2O, tau_O3, and the column-independent part f_CO2 * tau_CO2 + tau_CH4 + tau_N2O
         const size_t plane = n * NLAY;
@@ -1188,6 +1200,9 @@ static int lbl_advance(rcm_solver* s, int nsteps) {
     a.tau_clamp = s->tau_clamp;
     a.wvl_lo = s->d_lbl_lo;
     a.wvl_hi = s->d_lbl_hi;
+    a.wn_hi = s->d_lbl_lo + (size_t)s->lbl_nwvl;
+    a.wn_lo = s->d_lbl_lo + 2 * (size_t)s->lbl_nwvl;
+    a.bin_ok = reinterpret_cast<const int*>(s->d_lbl_lo + 3 * (size_t)s->lbl_nwvl);
     a.tau3 = s->d_lbl_tau5;
     a.h2o_ref = s->d_lbl_h2o_ref;
     a.o3_ref = s->lbl_has_o3_ref ? s->d_lbl_o3_ref : nullptr;

@@ -239,7 +239,11 @@ __global__ void __launch_bounds__(256) rcm_cplkavg_kernel(int n, const double* l
     __syncthreads();
     const unsigned tl = (unsigned)__cvta_generic_to_shared(stab + (threadIdx.x & (EXP_REP - 1)));
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        out[i] = narrow ? cplkavg_narrow(lo[i], hi[i], 1.0E7 / lo[i], 1.0E7 / hi[i], t[i], tl) : cplkavg_dev(lo[i], hi[i], t[i]);
+    {
+        const double whi = 1.0E7 / lo[i], wlo = 1.0E7 / hi[i];
+        const bool bin_ok = whi > wlo && wlo >= 0. && (whi - wlo) / whi < 1.e-2;
+        out[i] = narrow ? cplkavg_narrow(lo[i], hi[i], whi, wlo, bin_ok, t[i], tl) : cplkavg_dev(lo[i], hi[i], t[i]);
+    }
 }
 
 }  // namespace

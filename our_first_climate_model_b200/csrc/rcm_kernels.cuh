@@ -115,6 +115,9 @@ struct LblArgs {
     double co2_factor, tau_clamp;
     const double* __restrict__ wvl_lo;   // [nwvl] bin edges, nm
     const double* __restrict__ wvl_hi;
+    const double* __restrict__ wn_hi;    // [nwvl] 1e7 / wvl_lo, 1e7 / wvl_hi (wavenumbers of the bin edges, cm-1)
+    const double* __restrict__ wn_lo;
+    const int* __restrict__ bin_ok;      // [nwvl] the bin takes cplkavg's narrow-band (Simpson) branch
     const double* __restrict__ tau3;     // [3][nwvl][20]  H2O, O3, and f_CO2 * CO2 + CH4 + N2O (the column-independent part)
     const double* __restrict__ h2o_ref;  // [20]
     const double* __restrict__ o3_ref;   // [20] or NULL

@@ -64,13 +64,13 @@ __device__ __noinline__ double cplkavg_dev(double wvllo, double wvlhi, double t)
 // with the solver's exp (exp_scaled, <= 1 ulp like libm's) and division (div_fast, <= 1 ulp) instead of the
 // library routines, and with the two wavenumbers 1e7/lambda taken once per wavelength by the caller; every other
 // case goes to cplkavg_dev.  Same control flow and summation order, results within a few ulp of it.
-__device__ __forceinline__ double cplkavg_narrow(double wvllo, double wvlhi, double whi, double wlo, double t,
+// bin_ok: whi > wlo && wlo >= 0 && (whi - wlo) / whi < 1e-2 - a property of the bin, evaluated once per wavelength.
+__device__ __forceinline__ double cplkavg_narrow(double wvllo, double wvlhi, double whi, double wlo, bool bin_ok, double t,
                                                  unsigned tab_lane) {
     const double c2 = 1.438786, sigma = 5.67032E-8, pi = 3.14159265358979323846;
     const double vmax = 709.782712893384, sigdpi = sigma / pi, conc = 15. / (pi * pi * pi * pi);
     const double v0 = div_fast(c2 * wlo, t), v1 = div_fast(c2 * whi, t);
-    if (!(t >= 1.e-4 && whi > wlo && wlo >= 0. && v0 > DBL_EPSILON && v1 < vmax && (whi - wlo) / whi < 1.e-2))
-        return cplkavg_dev(wvllo, wvlhi, t);
+    if (!(bin_ok && t >= 1.e-4 && v0 > DBL_EPSILON && v1 < vmax)) return cplkavg_dev(wvllo, wvlhi, t);
     auto f = [&](double x) { return div_fast(x * x * x, exp_scaled<false>(x, L2E64, tab_lane) - 1.); };
     const double hh = v1 - v0;
     const double t4 = (t * t) * (t * t);
@@ -95,7 +95,10 @@ __device__ __forceinline__ double cplkavg_narrow(double wvllo, double wvlhi, dou
     const double ends = fa + fb;
     double prev = (ends + 4.0 * fm) * (del1 * (1. / 3.));
     double val = (((ends + 4.0 * fq1) + 2.0 * fm) + 4.0 * fq3) * (del2 * (1. / 3.));
-    if (fabs((val - prev) / val) <= 1.e-6) return sigdpi * t4 * conc * val;
+    // convergence test of cplkavg.cpp:172 without its division: |val - prev| <= 1e-6 |val| decides the same way except when
+    // the quotient rounds across 1e-6 exactly, and then both Simpson orders agree to 1e-6 anyway (an IEEE division here is
+    // ~25 instructions with its special-case paths, 3 % of the LBL kernel)
+    if (fabs(val - prev) <= 1.e-6 * fabs(val)) return sigdpi * t4 * conc * val;
     prev = val;
     for (int n = 3; n <= 10; ++n) {
         const double del = hh / (2 * n);
@@ -197,8 +200,11 @@ __global__ void __launch_bounds__(NT, 384 / NT) rcm_lbl_rt_kernel(const LblArgs 
         const bool real = w_any < a.nwvl;
         const int w = real ? w_any : a.nwvl - 1;
         double tau[HALF], Bo[HALF];
+        // the bin: edges [nm], wavenumbers 1e7 / lambda (cplkavg.cpp:141-142) and the narrow-band flag, all taken once per
+        // wavelength on the host (rcm_set_lbl_tables): two IEEE divisions per wavelength and thread otherwise
         const double lo = __ldg(a.wvl_lo + w), hi = __ldg(a.wvl_hi + w);
-        const double whi = 1.0E7 / lo, wlo = 1.0E7 / hi;  // cplkavg.cpp:141-142, once per wavelength
+        const double whi = __ldg(a.wn_hi + w), wlo = __ldg(a.wn_lo + w);
+        const bool bin_ok = __ldg(a.bin_ok + w) != 0;
         // tau = tau_H2O * s_H2O + tau_O3 * s_O3 + (f_CO2 * tau_CO2 + tau_CH4 + tau_N2O): the bracket does not depend on the
         // column and is summed once when the tables are uploaded (rcm_set_lbl_tables); two FMAs per layer and wavelength
         const double* t3 = a.tau3 + (size_t)w * NLAY;
@@ -212,13 +218,13 @@ __global__ void __launch_bounds__(NT, 384 / NT) rcm_lbl_rt_kernel(const LblArgs 
         // The band-integrated Planck function of the ten layers in a ROLLED loop through shared memory: inlined ten
         // times it made the kernel 9,900 instructions long and instruction fetch 6 % of its stalls.
 #pragma unroll 1
-        for (int j = 0; j < HALF; ++j) s_B[j * NT + tid] = cplkavg_narrow(lo, hi, whi, wlo, s_T[sb + j * C], tab_lane);
+        for (int j = 0; j < HALF; ++j) s_B[j * NT + tid] = cplkavg_narrow(lo, hi, whi, wlo, bin_ok, s_T[sb + j * C], tab_lane);
 #pragma unroll
         for (int j = 0; j < HALF; ++j) {
             const double B = s_B[j * NT + tid];
             Bo[j] = real ? B : 0.0;
         }
-        const double Bsurf = cplkavg_narrow(lo, hi, whi, wlo, s_Ts[c], tab_lane);
+        const double Bsurf = cplkavg_narrow(lo, hi, whi, wlo, bin_ok, s_Ts[c], tab_lane);
         sweep_item<CLAMPK>(tau, Bo, real ? Bsurf : 0.0, h, tab_lane, E1, E2, Eu20);
     }
     // partial fluxes of this wavelength chunk: part[chunk][col][0..20] = E_down, [21..41] = E_up
