@@ -396,6 +396,7 @@ def run_b200(args, rank, world, local_rank):
     e2e_s = max(e2e_ranks)
     e2e_value = world * units_per_step * args.steps / e2e_s
     olr_check = float(Eu[0, 0])
+    graph_stats = dict(zip(("captures", "replays"), solver.host_graph_stats()))
 
     # ---- strong scaling (BASELINE configs[3] as north_star states it): ONE 65,536-column ensemble over the ranks ----
     strong = None
@@ -479,8 +480,8 @@ def run_b200(args, rank, world, local_rank):
                     "ms_per_step_per_rank": {"min": 1e3 * min(e2e_ranks) / args.steps, "max": 1e3 * max(e2e_ranks) / args.steps},
                     "api": "rcm_step_host (pinned host buffers; T and Tsurf up, E_down/E_up/dE/T/Tsurf down every step; the "
                            "VMR rows went up once - H2O follows the feedback on the device; columns travel in 8 chunks through "
-                           "3 streams, copies overlap the step)",
-                    "numa": numa, "check_olr_col0": olr_check},
+                           "3 streams, copies overlap the step; from the second call on the pipeline is one CUDA graph launch)",
+                    "host_graph": graph_stats, "numa": numa, "check_olr_col0": olr_check},
             "strong": strong, "lbl": lbl,
             "gpu_launches": launches, "clocks": clocks, "fp64_peaks_Gops": peaks,
             "ensemble": {"toa_net_mean_Wm2": toa_mean, "collective": f"1 async all_gather of 4 doubles per step, ring of {args.ring}"

@@ -235,6 +235,8 @@ int rcm_cplkavg_device(rcm_solver* s, int n, const double* lo_nm, const double* 
 /* Introspection for the bench: kernels launched so far, and FP64-pipe microbenchmarks
  * (result in 1e9 thread-instructions/s: which = 0 DFMA, 1 exp(), 2 divide, 3 solver exp). */
 long rcm_launch_count(const rcm_solver* s);
+/* rcm_step_host in steady state replays its chunk pipeline as one CUDA graph: how often it was captured / replayed. */
+int rcm_host_graph_stats(const rcm_solver* s, long* captures, long* replays);
 int rcm_fp64_microbench(rcm_solver* s, int which, double* ginstr_per_s);
 /* Average device time (ms) of the fused step kernel over the launches since the last reset,
  * measured with CUDA events on the launching stream. */

@@ -451,6 +451,12 @@ class Solver:
     def launch_count(self) -> int:
         return int(_lib.rcm_launch_count(self._h))
 
+    def host_graph_stats(self):
+        """(captures, replays) of step_host's steady-state CUDA graph."""
+        c, r = C.c_long(0), C.c_long(0)
+        _check(_lib.rcm_host_graph_stats(self._h, C.byref(c), C.byref(r)), self._h)
+        return c.value, r.value
+
     def fp64_microbench(self, which: int) -> float:
         v = C.c_double(0)
         _check(_lib.rcm_fp64_microbench(self._h, C.c_int(which), C.byref(v)), self._h)

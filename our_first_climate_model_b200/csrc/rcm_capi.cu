@@ -78,6 +78,19 @@ struct rcm_solver {
     cudaEvent_t pipe_done[3] = {nullptr, nullptr, nullptr}, pipe_start = nullptr;
     // ... of the split path: uploads + K5 prep (high priority), unit kernels alternating on two streams, K5 finish + downloads
     // (high priority); one event per chunk and stage
+    // the steady-state call of that pipeline captured as ONE CUDA graph (about 200 runtime calls per step otherwise - with
+    // eight ranks on one host the CPU side of the pipeline became its critical path); `sig` + host pointers identify what the
+    // graph has baked in, anything else re-captures
+    struct HostGraph {
+        cudaGraphExec_t exec = nullptr;
+        SplitArgs sig{};
+        const void* host[7] = {};
+        const void* dev[4] = {};
+        double dT_converged = 0.0;
+        int ncol = 0, nchunk = 0, nkernels = 0;
+        long captures = 0, replays = 0;
+        bool failed = false;
+    } hg;
     cudaStream_t sp_up = nullptr, sp_rt[2] = {nullptr, nullptr}, sp_down = nullptr;
     cudaEvent_t sp_prep[24] = {}, sp_rtdone[24] = {}, sp_end = nullptr;
     double kt_ms = 0.0;
@@ -678,10 +691,13 @@ int step_host_split(rcm_solver* s, int nchunk, const double* Tlayer_in, const do
         for (int c0 = per; c0 < s->ncol; c0 += per) bounds[nb++] = c0;
     }
     bounds[nb] = s->ncol;
-    CU(cudaEventRecord(s->sp_end, s->stream));  // everything queued on the solver's stream so far comes first
-    for (cudaStream_t q : {s->sp_up, s->sp_rt[0], s->sp_rt[1], s->sp_down}) CU(cudaStreamWaitEvent(q, s->sp_end, 0));
     const size_t D = sizeof(double);
     const int na = s->nactive;
+    // everything of one call, from the fork off the solver's stream to the scalar reduction after the join
+    auto enqueue = [&](bool timed) -> int {
+    int nk = 0;
+    CU(cudaEventRecord(s->sp_end, s->stream));  // everything queued on the solver's stream so far comes first
+    for (cudaStream_t q : {s->sp_up, s->sp_rt[0], s->sp_rt[1], s->sp_down}) CU(cudaStreamWaitEvent(q, s->sp_end, 0));
     for (int k = 0; k < nb; ++k) {
         const int c0 = bounds[k], n = bounds[k + 1] - c0;
         if (n <= 0) continue;
@@ -705,8 +721,9 @@ int step_host_split(rcm_solver* s, int nchunk, const double* Tlayer_in, const do
         q = s->sp_rt[k % 2];
         CU(cudaStreamWaitEvent(q, s->sp_prep[k], 0));
         CU(cudaMemsetAsync(a.counter, 0, sizeof(unsigned), q));
-        st = split_rt(s, a, nsm, q, true);
+        st = split_rt(s, a, nsm, q, timed);
         if (st != RCM_OK) return st;
+        nk += 3;
         CU(cudaEventRecord(s->sp_rtdone[k], q));
         q = s->sp_down;
         CU(cudaStreamWaitEvent(q, s->sp_rtdone[k], 0));
@@ -725,6 +742,73 @@ int step_host_split(rcm_solver* s, int nchunk, const double* Tlayer_in, const do
     CU(cudaStreamWaitEvent(s->stream, s->sp_end, 0));
     CU(rcm_launch_reduce_diag(s->d_diag, 1, s->ncol, s->p.dT_converged, s->d_red, s->d_ticket, s->d_scalars, s->stream));
     s->launches += 1;
+    s->hg.nkernels = nk + 1;
+    return RCM_OK;
+    };  // enqueue
+
+    // Steady state (not the first iteration, VMR rows of the tile blocks current, no VMR upload): the call is the same
+    // sequence every time - launch it as one graph.  RCM_NO_GRAPH=1 keeps the direct calls (comparison).
+    const bool steady = s->step_index > 0 && s->tile_vmr_valid && !vmr_active_in && !s->hg.failed && !std::getenv("RCM_NO_GRAPH");
+    bool launched = false;
+    if (steady) {
+        rcm_solver::HostGraph& g = s->hg;
+        const SplitArgs sig = split_args(s, 0, s->ncol, 1);
+        const void* host[7] = {Tlayer_in, Tsurf_in, E_down, E_up, dE, Tlayer_out, Tsurf_out};
+        const void* dev[4] = {s->d_diag, s->d_red, s->d_ticket, s->d_scalars};
+        const bool same = g.exec && std::memcmp(&g.sig, &sig, sizeof(sig)) == 0 && std::memcmp(g.host, host, sizeof(host)) == 0 &&
+                          std::memcmp(g.dev, dev, sizeof(dev)) == 0 && g.dT_converged == s->p.dT_converged && g.ncol == s->ncol &&
+                          g.nchunk == nchunk;
+        if (!same) {
+            if (g.exec) cudaGraphExecDestroy(g.exec);
+            g.exec = nullptr;
+            cudaGraph_t graph = nullptr;
+            const long launches0 = s->launches;
+            // asynchronous copies can only be captured from / to page-locked host memory: with pageable buffers stay direct
+            bool ok = true;
+            for (const void* hp : host) {
+                cudaPointerAttributes at{};
+                if (hp && (cudaPointerGetAttributes(&at, hp) != cudaSuccess || at.type != cudaMemoryTypeHost)) ok = false;
+            }
+            cudaGetLastError();
+            ok = ok && cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+            if (ok) {
+                ok = enqueue(false) == RCM_OK;
+                ok = (cudaStreamEndCapture(s->stream, &graph) == cudaSuccess) && ok && graph;
+            }
+            s->launches = launches0;  // captured, not launched
+            g.captures += 1;
+            if (ok) ok = cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess;
+            if (graph) cudaGraphDestroy(graph);
+            if (!ok) {  // direct calls: for this call with pageable buffers, for good when the capture itself failed
+                cudaGetLastError();
+                g.exec = nullptr;
+                bool pinned = true;
+                for (const void* hp : host) {
+                    cudaPointerAttributes at{};
+                    if (hp && (cudaPointerGetAttributes(&at, hp) != cudaSuccess || at.type != cudaMemoryTypeHost)) pinned = false;
+                }
+                cudaGetLastError();
+                if (pinned) g.failed = true;
+            } else {
+                g.sig = sig;
+                std::memcpy(g.host, host, sizeof(host));
+                std::memcpy(g.dev, dev, sizeof(dev));
+                g.dT_converged = s->p.dT_converged;
+                g.ncol = s->ncol;
+                g.nchunk = nchunk;
+            }
+        }
+        if (g.exec) {
+            CU(cudaGraphLaunch(g.exec, s->stream));
+            s->launches += g.nkernels;
+            g.replays += 1;
+            launched = true;
+        }
+    }
+    if (!launched) {
+        st = enqueue(true);
+        if (st != RCM_OK) return st;
+    }
     s->step_index += 1;
     s->tau_valid = false;
     s->tile_vmr_valid = true;
@@ -805,6 +889,7 @@ int rcm_destroy(rcm_solver* s) {
         if (s->sp_rtdone[i]) cudaEventDestroy(s->sp_rtdone[i]);
     }
     if (s->sp_end) cudaEventDestroy(s->sp_end);
+    if (s->hg.exec) cudaGraphExecDestroy(s->hg.exec);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     delete s;
     return RCM_OK;
@@ -1529,6 +1614,13 @@ int rcm_cplkavg_device(rcm_solver* s, int n, const double* lo_nm, const double* 
 }
 
 long rcm_launch_count(const rcm_solver* s) { return s ? s->launches : 0; }
+
+int rcm_host_graph_stats(const rcm_solver* s, long* captures, long* replays) {
+    if (!s || !captures || !replays) return RCM_ERR_ARG;
+    *captures = s->hg.captures;
+    *replays = s->hg.replays;
+    return RCM_OK;
+}
 
 int rcm_fp64_microbench(rcm_solver* s, int which, double* gops) {
     if (!s || !gops || which < 0 || which > 3) return RCM_ERR_ARG;

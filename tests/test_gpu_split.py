@@ -149,3 +149,39 @@ def test_perturbed_members_reach_the_reference_equilibrium(rcm, golden, golden_e
     assert dT.max() < 1e-6 and relerr(st["E_up"], golden_eq["E_up"]) < 1e-9
     np.testing.assert_allclose(st["h2o"], golden_eq["h2o"], rtol=1e-8)
     assert sc[-1, 1] < 1e-2 and golden_eq["Tsurf"].max() - golden_eq["Tsurf"].min() > 10.0  # members really differ
+
+
+def test_step_host_graph_path_is_bit_identical(rcm):
+    """From the second call on rcm_step_host launches its whole chunk pipeline as ONE captured CUDA graph (page-locked host
+    buffers; the first call and calls with pageable buffers stay direct).  Five consecutive calls - direct, capture +
+    launch, three relaunches - against resident stepping, bit for bit; then other output buffers (re-capture)."""
+    import torch
+    ncol = 40000
+    st = ensemble(rcm, ncol, 9)
+    s = rcm.Solver(0)
+    s.set_repwvl_table_from(rcm.Table(table_path(100)))
+    s.set_columns(st["plevel"], st["Tlayer"], st["Tsurf"], st["vmr9"], st["rel_hum"])
+    ref = []
+    for _ in range(6):
+        s.advance(1)
+        ref.append(s.get_state())
+    pin = lambda *shape: torch.empty(*shape, dtype=torch.float64).pin_memory()
+    T_in, Ts_in, v_in = pin(ncol, 20), pin(ncol), pin(ncol, s.nactive, 20)
+    outs = [[pin(ncol, 21), pin(ncol, 21), pin(ncol, 20), pin(ncol, 20), pin(ncol)] for _ in range(2)]
+    active = [k for k in range(9) if s.params.species_mask >> k & 1]
+    T_in.copy_(torch.from_numpy(st["Tlayer"]))
+    Ts_in.copy_(torch.from_numpy(st["Tsurf"]))
+    v_in.copy_(torch.from_numpy(np.ascontiguousarray(st["vmr9"][:, active, :])))
+    s.set_columns(st["plevel"], st["Tlayer"], st["Tsurf"], st["vmr9"], st["rel_hum"])
+    l0 = s.launch_count()
+    for k in range(6):
+        o = outs[0] if k < 5 else outs[1]                      # the sixth call writes to other buffers: re-capture
+        ptrs = [T_in.data_ptr(), Ts_in.data_ptr(), v_in.data_ptr() if k == 0 else 0] + [t.data_ptr() for t in o]
+        s.step_host_ptrs(*ptrs)
+        for name, t in zip(("E_down", "E_up", "dE", "Tlayer", "Tsurf"), o):
+            assert np.array_equal(t.numpy(), ref[k][name]), (k, name)
+        T_in.copy_(o[3])                                          # the next call continues from this call's result
+        Ts_in.copy_(o[4])
+    assert s.launch_count() - l0 >= 6 * (3 * 8 + 1)               # graph launches count their kernels too
+    assert s.host_graph_stats() == (2, 5)                         # captured at call 2 and call 6, replayed 5 times
+    s.close()
