@@ -225,6 +225,14 @@ int rcm_column_count(const rcm_solver* s); /* columns currently loaded (rcm_set_
  * the reference's header line (main.cpp:528) first.  Host only. */
 int rcm_write_profiles(const char* path, int append, int header, int ncol, const double* plevel_hPa,
                        const double* Tlayer, const float* time_h, int column_ids);
+/* One iteration with HOST buffers (what a caller that keeps its state on the host does per step of main.cpp:531-583):
+ * uploads Tlayer_in [ncol][20], Tsurf_in [ncol], vmr_active_in [ncol][nactive][20] - each only when not NULL (no VMR upload: the
+ * rows of the previous call stay, H2O following the feedback on the device as in the reference loop), runs the step, downloads
+ * E_down / E_up [ncol][21], dE / Tlayer_out [ncol][20], Tsurf_out [ncol] (each may be NULL = not wanted); synchronous.
+ * On the split path the columns travel in chunks through upload / compute / download streams; with page-locked buffers the
+ * pipeline of a steady-state call (second call on, same pointers, no VMR upload) is replayed as one CUDA graph - results are
+ * bit-identical to rcm_advance(1) either way.  Environment: RCM_NO_GRAPH=1 keeps the direct calls, RCM_PIPE_CHUNKS=n sets the
+ * chunk count.  Errors: RCM_ERR_ARG (no solver), RCM_ERR_STATE without columns / table, RCM_ERR_CUDA. */
 int rcm_step_host(rcm_solver* s, const double* Tlayer_in, const double* Tsurf_in, const double* vmr_active_in,
                   double* E_down, double* E_up, double* dE, double* Tlayer_out, double* Tsurf_out);
 
