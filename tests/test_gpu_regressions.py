@@ -115,3 +115,39 @@ def test_planck_exponent_stays_in_range(rcm, golden):
         s.set_spectral_grid(np.array([1100.0, 5000.0]), np.array([1.0, 1.0]))
     finally:
         s.close()
+
+
+def test_abi_refuses_bad_calls_without_touching_the_device(rcm, golden):
+    """Error behaviour of the C ABI: status codes, never exit / throw; a refused call leaves the
+    solver usable.  The reference's entry points have no such checks ('size mismatch only prints')."""
+    import ctypes as C
+    L = rcm.load_library()
+    ARG, STATE = 1, 2
+    assert L.rcm_status_string(ARG) and L.rcm_status_string(STATE)
+    s = rcm.Solver(0)
+    try:
+        h = s._h
+        sc = (rcm.StepScalars * 4)()
+        # nothing loaded yet
+        assert L.rcm_advance(h, 1, sc) == STATE and b"table and columns" in L.rcm_last_error(h)
+        assert L.rcm_get_state(h, None, None, None, None, None, None, None, None) == STATE
+        assert L.rcm_step_host(h, None, None, None, None, None, None, None, None) != 0
+        assert L.rcm_save_checkpoint(h, b"/tmp/never_written.ckpt") != 0
+        # NULL handle / NULL or empty inputs
+        assert L.rcm_advance(None, 1, sc) == ARG and L.rcm_column_count(None) <= 0
+        d = lambda a: np.ascontiguousarray(a, dtype=np.float64).ctypes.data_as(C.c_void_p)
+        pl, T, Ts, v, rh = (golden[k] for k in ("plevel", "Tlayer", "Tsurf", "vmr9", "rel_hum"))
+        assert L.rcm_set_columns(h, 0, d(pl), d(T), d(Ts), d(v), d(rh)) == ARG
+        assert L.rcm_set_columns(h, -3, d(pl), d(T), d(Ts), d(v), d(rh)) == ARG
+        assert L.rcm_set_columns(h, 4, d(pl), None, d(Ts), d(v), d(rh)) == ARG
+        # columns without a table: still a state error, then the normal sequence works on the same handle
+        s.set_columns(pl, T[:4], Ts[:4], v[:4], rh[:4])
+        assert L.rcm_advance(h, 1, sc) == STATE
+        s.set_repwvl_table_from(rcm.Table(table_path(20)))
+        assert L.rcm_advance(h, 0, sc) == ARG and L.rcm_advance(h, -1, sc) == ARG
+        assert L.rcm_advance(h, 1, sc) == 0
+        st = s.get_state()
+        assert abs(st["E_up"][0, 0] - golden["s1_E_up_20"][0, 0]) < 1e-10 * st["E_up"][0, 0]
+        assert s.launch_count() > 0
+    finally:
+        s.close()
