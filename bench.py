@@ -479,7 +479,7 @@ def run_b200(args, rank, world, local_rank):
                     "ms_per_step": 1e3 * e2e_s / args.steps,
                     "ms_per_step_per_rank": {"min": 1e3 * min(e2e_ranks) / args.steps, "max": 1e3 * max(e2e_ranks) / args.steps},
                     "api": "rcm_step_host (pinned host buffers; T and Tsurf up, E_down/E_up/dE/T/Tsurf down every step; the "
-                           "VMR rows went up once - H2O follows the feedback on the device; columns travel in 8 chunks through "
+                           "VMR rows went up once - H2O follows the feedback on the device; columns travel in 10 chunks (eight, the first and the last split again) through "
                            "3 streams, copies overlap the step; from the second call on the pipeline is one CUDA graph launch)",
                     "host_graph": graph_stats, "numa": numa, "check_olr_col0": olr_check},
             "strong": strong, "lbl": lbl,
