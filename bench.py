@@ -41,7 +41,7 @@ ALG_EXP, ALG_DIV, ALG_FMA = 31, 33, 520
 # new capture the line says "stale": true (and tests/test_host.py fails).
 CAPTURE_JSON = os.path.join(ROOT, "profiles", "roofline_capture.json")
 KERNEL_SOURCES = ["rcm_kernels.cuh", "rcm_device_math.cuh", "rcm_step_kernel.cuh", "rcm_split_kernels.cuh",
-                  "rcm_lbl_kernels.cuh"]
+                  "rcm_split_unit_loop.inc", "rcm_lbl_kernels.cuh"]
 
 
 def kernel_sources_sha():

@@ -128,6 +128,13 @@ int rcm_set_params(rcm_solver* s, const rcm_params* p);
  * 3a = 7b take their transmissions as powers of ONE exp at a virtual node (30 angles: 4 of the 20 exp's per layer
  * and wavelength become 3-4 multiplications; same mu values, ~1e-14 relative). */
 #define RCM_OPT_ANGLE_PAIRS 4
+/* RCM_OPT_PATH (default 0): 0 = split path ((tile, wavelength-split) units, results independent of shard / GPU count),
+ * 1 = the fused tile kernel of round 1 (comparison).  RCM_OPT_MULTI_STEP (default 1, split path): rcm_advance(n >= 2) runs
+ * its n steps as ONE persistent launch with per-tile step flags instead of kernel boundaries where a step is only a few
+ * rounds of work units per CTA (up to ~34,000 columns per GPU); 0 = always three launches per step, 2 = always one launch.
+ * Bit-identical either way. */
+#define RCM_OPT_PATH 5
+#define RCM_OPT_MULTI_STEP 6
 int rcm_set_option(rcm_solver* s, int option, int value);
 /* cudaStream_t to launch on (NULL = the solver's own stream). */
 int rcm_set_stream(rcm_solver* s, void* cuda_stream);

@@ -68,6 +68,9 @@ struct rcm_solver {
     unsigned char* d_tile = nullptr;    // [tiles][TILE_BYTES]
     double* d_spart = nullptr;          // [tiles][nsplit][42][16]
     unsigned* d_counter = nullptr;      // [4] work counters: the solver's stream and the three pipeline streams
+    unsigned* d_multi = nullptr;        // [2][tile_cap] per-tile counters / step flags of the multi-step unit kernel
+    size_t multi_cap = 0;
+    int opt_multi = 1;                  // option 6: blocks of steps as ONE launch of the multi-step unit kernel
     size_t tile_cap = 0, spart_cap = 0;
     bool tile_vmr_valid = false;        // the constant species' rows of the tile blocks are current
     std::vector<double> stage;  // host packing buffer
@@ -503,6 +506,12 @@ int ensure_split(rcm_solver* s) {
         CU(dalloc(s->d_spart, need_part));
         s->spart_cap = need_part;
     }
+    if (tiles > s->multi_cap || !s->d_multi) {
+        if (s->d_multi) CU(cudaFree(s->d_multi));
+        s->d_multi = nullptr;
+        CU(cudaMalloc((void**)&s->d_multi, 2 * tiles * sizeof(unsigned)));
+        s->multi_cap = tiles;
+    }
     if (!s->d_dTstat) CU(dalloc(s->d_dTstat, (size_t)s->cap));
     if (!s->d_counter) {
         CU(dalloc(s->d_counter, (size_t)4));
@@ -606,6 +615,26 @@ int split_advance(rcm_solver* s, int nsteps) {
     CU(rcm_launch_split_col(a, f, s->stream));
     s->launches += 1;
     s->tile_vmr_valid = true;
+    // ... where a step is only a few rounds of units per CTA (8,192 columns: 5.8; the partial last round and the K5 launches
+    // of every step cost 7 % there); with many rounds per step the separate K5 kernel is the cheaper one (65,536 columns:
+    // 46 rounds, one launch per block 0.9 % slower than three per step).  opt_multi = 2 forces it (tests).
+    static const int multi_rounds = std::getenv("RCM_MULTI_ROUNDS") ? std::atoi(std::getenv("RCM_MULTI_ROUNDS")) : 24;
+    const int grid1 = split_grid(s, a, nsm);
+    const bool few_rounds = a.nunits < (long long)multi_rounds * grid1;
+    if (nsteps >= 2 && (s->opt_multi == 2 || (s->opt_multi == 1 && few_rounds))) {
+        // a block of steps as ONE launch: (step, unit) items in step-major order, per-tile step flags instead of kernel
+        // boundaries, the K5 body run by the CTA that completes a tile's step (rcm_split_multi_kernel)
+        SplitMultiArgs m{};
+        m.nsteps = nsteps;
+        m.done = s->d_multi;
+        m.ready = s->d_multi + a.ntiles;
+        CU(cudaMemsetAsync(s->d_multi, 0, 2 * (size_t)a.ntiles * sizeof(unsigned), s->stream));
+        SplitArgs am = a;
+        am.quota = 1 << 30;
+        CU(rcm_launch_split_multi(am, m, split_grid(s, am, nsm), s->stream));
+        s->launches += 1;
+        return RCM_OK;
+    }
     for (int k = 0; k < nsteps; ++k) {
         st = split_rt(s, a, nsm, s->stream, k < 4);  // long blocks: the first steps are timed, the rest run without event records
         if (st != RCM_OK) return st;
@@ -872,7 +901,7 @@ int rcm_destroy(rcm_solver* s) {
     void* ptrs[] = {s->d_coef3, s->d_xsec_file, s->d_coef, s->d_species, s->d_planck_c, s->d_planck_k, s->d_exp_tab, s->d_T, s->d_Ts, s->d_vmr, s->d_rh,
                     s->d_Tprev, s->d_time, s->d_lbl_lo, s->d_lbl_hi, s->d_lbl_tau5, s->d_lbl_h2o_ref, s->d_lbl_o3_ref, s->d_sH, s->d_sO,
                     s->d_dTstat, s->d_part, s->d_Ed, s->d_Eu, s->d_dE, s->d_dt, s->d_diag, s->d_scalars, s->d_red, s->d_tau,
-                    s->d_lowpos, s->d_solar_col, s->d_cloud_col, s->d_ticket, s->d_tile, s->d_spart, s->d_counter};
+                    s->d_lowpos, s->d_solar_col, s->d_cloud_col, s->d_ticket, s->d_tile, s->d_spart, s->d_counter, s->d_multi};
     for (void* q : ptrs)
         if (q) cudaFree(q);
     for (auto& e : s->ev_free) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -939,6 +968,10 @@ int rcm_set_option(rcm_solver* s, int option, int value) {
     if (option == 5) {
         s->opt_path = value ? 1 : 0;
         s->tile_vmr_valid = false;
+        return RCM_OK;
+    }
+    if (option == 6) {
+        s->opt_multi = value < 0 ? 0 : value > 2 ? 2 : value;
         return RCM_OK;
     }
     return fail(s, RCM_ERR_ARG, "unknown option");

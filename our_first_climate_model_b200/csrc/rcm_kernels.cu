@@ -311,6 +311,14 @@ cudaError_t rcm_launch_split_rt(const SplitArgs& a, int grid, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+cudaError_t rcm_launch_split_multi(const SplitArgs& a, const SplitMultiArgs& m, int grid, cudaStream_t st) {
+    auto kern = a.clampk ? rcm_split_multi_kernel<true> : rcm_split_multi_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPLIT_SMEM);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, SPLIT_NT, SPLIT_SMEM, st>>>(a, m);
+    return cudaGetLastError();
+}
+
 size_t rcm_reduce_scratch_doubles(int nsteps) { return (size_t)nsteps * RED_BLOCKS * 4; }
 
 // scratch: rcm_reduce_scratch_doubles(capacity) doubles; ticket: one counter per step of the CAPACITY the buffers were

@@ -157,11 +157,17 @@ struct SplitColFlags {
     int write_out;      // store E_down, E_up, dE, dt of the finished step
     int diag_step;      // row of diag the finished step writes
 };
+struct SplitMultiArgs {  // the multi-step unit kernel (rcm_split_multi_kernel)
+    int nsteps;          // steps of this launch; diag rows 0 .. nsteps-1
+    unsigned* done;      // [ntiles] units finished per tile, all steps of the launch (zero at launch)
+    unsigned* ready;     // [ntiles] step the tile is prepared for (zero at launch: the K5 prep in front has run)
+};
 size_t rcm_split_tile_bytes();
 size_t rcm_split_part_doubles();
 int rcm_split_ipu();
 cudaError_t rcm_launch_split_col(const SplitArgs& a, const SplitColFlags& f, cudaStream_t st);
 cudaError_t rcm_launch_split_rt(const SplitArgs& a, int grid, cudaStream_t st);
+cudaError_t rcm_launch_split_multi(const SplitArgs& a, const SplitMultiArgs& m, int grid, cudaStream_t st);
 
 enum { MODE_STEP = 0, MODE_TAU = 1, MODE_RT = 2 };
 

@@ -59,15 +59,27 @@ constexpr int SPLIT_PART = 2 * NLEV * SPLIT_C;  // doubles of one unit's partial
 // one per phase - with a load in front of every phase the kernel took 260 us per 65,536 columns, latency-bound at four
 // CTAs per SM); the phases then run out of shared memory and results leave as contiguous tile rows.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SPLIT_COL_NT, 8) rcm_split_col_kernel(const SplitArgs a, const SplitColFlags f) {
+struct SplitColSmem {
+    double sT[NLAY * SPLIT_C], sTh[NLAY * SPLIT_C], sPrev[NLAY * SPLIT_C], sRh[NLAY * SPLIT_C], sEd[NLEV * SPLIT_C],
+        sEu[NLEV * SPLIT_C], sdE[NLAY * SPLIT_C], sdt[SPLIT_C], sTs[SPLIT_C], sSol[SPLIT_C], sStat[SPLIT_C];
+    int sit[NLAY * SPLIT_C], sitmin[NLAY], sout[NLAY + 1];
+};
+
+// The body for one tile, by the 128 threads of a CTA: the K5 kernel's (STANDALONE), and the multi-step unit kernel's, where
+// the CTA that finishes a tile's last unit of a step runs it in place.  State written by an earlier call of this function
+// may come from another SM: everything mutable is loaded past L1 (__ldcg).
+template <bool STANDALONE>
+__device__ __forceinline__ void split_col_body(const SplitArgs& a, const SplitColFlags f, const int tile, SplitColSmem& cs) {
     constexpr int C = SPLIT_C, NT = SPLIT_COL_NT, LC = NLAY * C;
-    __shared__ double sT[LC], sTh[LC], sPrev[LC], sRh[LC], sEd[NLEV * C], sEu[NLEV * C], sdE[LC], sdt[C], sTs[C], sSol[C], sStat[C];
-    __shared__ int sit[LC], sitmin[NLAY], sout[NLAY + 1];
+    double* const sT = cs.sT; double* const sTh = cs.sTh; double* const sPrev = cs.sPrev; double* const sRh = cs.sRh;
+    double* const sEd = cs.sEd; double* const sEu = cs.sEu; double* const sdE = cs.sdE; double* const sdt = cs.sdt;
+    double* const sTs = cs.sTs; double* const sSol = cs.sSol; double* const sStat = cs.sStat;
+    int* const sit = cs.sit; int* const sitmin = cs.sitmin; int* const sout = cs.sout;
     int extrap = 0;  // some temperature of the tile lies outside the table's nodes: cross sections are extrapolated
-    const int tid = threadIdx.x, tile = blockIdx.x;
+    const int tid = threadIdx.x;
     const int col0 = tile * C, ncl = min(C, a.ncol - col0);
     const int nact = cst.nactive, nwvl = cst.nwvl;
-    if (tile == 0 && tid == 0 && a.counter) *a.counter = 0u;  // work counter of the unit kernel that follows on this stream
+    if (STANDALONE && tile == 0 && tid == 0 && a.counter) *a.counter = 0u;  // work counter of the unit kernel that follows on this stream
     double* const tb = reinterpret_cast<double*>(a.tile + (size_t)tile * TILE_BYTES);
     int* const tbi = reinterpret_cast<int*>(tb + TB_DOUBLES);
     const bool feedback = f.prep && !f.first && a.h2o_slot >= 0;
@@ -76,15 +88,15 @@ __global__ void __launch_bounds__(SPLIT_COL_NT, 8) rcm_split_col_kernel(const Sp
     for (int i = tid; i < LC; i += NT) {
         const int cc = i / NLAY, l = i % NLAY;
         const size_t gi = (size_t)(col0 + (cc < ncl ? cc : 0)) * NLAY + l;
-        sT[l * C + cc] = a.Tlayer[gi];
-        if (f.prep) sPrev[l * C + cc] = a.Tprev[gi];
+        sT[l * C + cc] = __ldcg(a.Tlayer + gi);
+        if (f.prep) sPrev[l * C + cc] = __ldcg(a.Tprev + gi);
         if (feedback) sRh[l * C + cc] = a.rel_hum[gi];
     }
     if (tid < C) {
         const int col = col0 + (tid < ncl ? tid : 0);
-        sTs[tid] = a.Tsurf[col];
+        sTs[tid] = __ldcg(a.Tsurf + col);
         sSol[tid] = a.solar_col ? a.solar_col[col] : cst.solar_irr;
-        if (f.finish) sStat[tid] = a.dTstat[col];
+        if (f.finish) sStat[tid] = __ldcg(a.dTstat + col);
     }
     if (f.finish) {
         // K4 tail: the step's partial fluxes, summed over the splits in index order
@@ -93,7 +105,7 @@ __global__ void __launch_bounds__(SPLIT_COL_NT, 8) rcm_split_col_kernel(const Sp
             const int row = i / C;
             double sum = 0.0;
             if (row != NLAY)
-                for (int sp = 0; sp < a.nsplit; ++sp) sum += part[(size_t)sp * SPLIT_PART + i];
+                for (int sp = 0; sp < a.nsplit; ++sp) sum += __ldcg(part + (size_t)sp * SPLIT_PART + i);
             if (row < NLAY) sEd[i + C] = sum;
             else if (row == NLAY) sEd[i % C] = 0.0;  // E_down at the top of the atmosphere stays 0 (main.cpp:300)
             else sEu[i - NLEV * C] = sum;
@@ -122,7 +134,7 @@ __global__ void __launch_bounds__(SPLIT_COL_NT, 8) rcm_split_col_kernel(const Sp
             sdt[tid] = dt;
             if (tid < ncl) {
                 const int col = col0 + tid;
-                a.time_h[col] += (float)dt / 3600;  // main.cpp:581
+                a.time_h[col] = __ldcg(a.time_h + col) + (float)dt / 3600;  // main.cpp:581
                 if (a.diag) {
                     double* dg = a.diag + ((size_t)f.diag_step * a.diag_ncol + col) * 4;
                     dg[0] = sSol[tid] - sEu[tid];
@@ -258,6 +270,38 @@ __global__ void __launch_bounds__(SPLIT_COL_NT, 8) rcm_split_col_kernel(const Sp
     }
 }
 
+// for the multi-step unit kernel: a real call, so that the body's registers and code stay out of the unit loop's allocation
+// and scheduling (inlined, ptxas arranged the angle loop differently and the units ran 15 % slower)
+__device__ __noinline__ void split_col_body_call(const SplitArgs& a, const SplitColFlags f, const int tile, SplitColSmem& cs) {
+    split_col_body<false>(a, f, tile, cs);
+}
+
+__global__ void __launch_bounds__(SPLIT_COL_NT, 8) rcm_split_col_kernel(const SplitArgs a, const SplitColFlags f) {
+    __shared__ SplitColSmem cs;
+    split_col_body<true>(a, f, blockIdx.x, cs);
+}
+
+// ---- per-tile step flags of the multi-step kernel (gpu scope) ----
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// A real call: inlined at the top of the unit loop, this spin loop made ptxas arrange the angle loop differently (units 15 %
+// slower).  A step flag that never comes is a bug: fail loudly after seconds instead of hanging the GPU.
+__device__ __noinline__ void wait_tile_ready(const unsigned* flag, unsigned step) {
+    unsigned spins = 0;
+    while (ld_acquire_gpu(flag) < step) {
+        __nanosleep(128);
+        if (++spins > (1u << 23)) __trap();
+    }
+    asm volatile("fence.proxy.async;" ::: "memory");  // the block was written through the generic proxy (another SM)
+}
+
 // ---- TMA bulk copy + mbarrier (one elected thread issues, everybody waits on the phase) -------------------------
 __device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
@@ -288,165 +332,28 @@ __device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned phase) {
 // Shared memory: exp table 8 KB | four row buffers 4 x 7,680 B (after the wavelength loop: the groups' partial fluxes)
 // | tile block 23,552 B | Planck factors 2 KB | mbarrier, next unit.
 // ------------------------------------------------------------------------------------------
-constexpr size_t SPLIT_SMEM = (size_t)EXP_TAB * EXP_REP * 8 + (size_t)SPLIT_G * ROWBUF3 + TILE_BYTES + 2 * PLK_MAX * 8 + 16;
+constexpr size_t SPLIT_SMEM = (size_t)EXP_TAB * EXP_REP * 8 + (size_t)SPLIT_G * ROWBUF3 + TILE_BYTES + 2 * PLK_MAX * 8 + 48;  // + mbarrier (8) + s_next[8]
 static_assert(SPLIT_PART * 8 <= ROWBUF3, "a warp's row buffer carries its partial fluxes after the wavelength loop");
 
+static_assert(sizeof(SplitColSmem) <= (size_t)SPLIT_G * ROWBUF3, "the K5 body of the multi-step kernel works in the row buffers");
+static_assert(SPLIT_COL_NT == SPLIT_NT, "the multi-step kernel runs the K5 body with its own CTA");
+
+// MULTI: one launch runs m.nsteps steps.  Work items are (step, unit) in step-major order from the same counter; a unit of
+// step n waits for ready[tile] >= n, and the CTA that completes a tile's last unit of step n runs the K5 body for it (finish
+// n, prep n + 1) and publishes ready[tile] = n + 1.  Dependencies point to lower item numbers only and every handed-out item
+// is held by a running CTA, so the smallest unfinished item can always proceed: no deadlock whatever the grid.  The order of
+// every addition is that of the one-step kernels - results are bit-identical - but there is no kernel boundary per step: no
+// partial last round per step (8,192 columns: 5.77 rounds), K5 off the critical path.
 template <bool CLAMPK>
 __global__ void __launch_bounds__(SPLIT_NT, 3) rcm_split_rt_kernel(const SplitArgs a) {
-    constexpr int C = SPLIT_C, NT = SPLIT_NT, G = SPLIT_G, NACT = 5;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double* const s_exp = reinterpret_cast<double*>(smem_raw);
-    unsigned char* const s_rows = smem_raw + (size_t)EXP_TAB * EXP_REP * 8;
-    double* const tb = reinterpret_cast<double*>(s_rows + (size_t)G * ROWBUF3);
-    const int* const tbi = reinterpret_cast<const int*>(tb + TB_DOUBLES);
-    double* const s_plk = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(tb) + TILE_BYTES);
-    unsigned long long* const s_mbar = reinterpret_cast<unsigned long long*>(s_plk + 2 * PLK_MAX);
-    volatile int* const s_next = reinterpret_cast<volatile int*>(s_mbar + 1);
+#define RCM_SPLIT_MULTI 0
+#include "rcm_split_unit_loop.inc"
+#undef RCM_SPLIT_MULTI
+}
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int h = tid & 1, q = tid >> 1, c = q % C, g = q / C;  // g == warp: one warp per wavelength group
-    const int sb = tbd(h * HALF, c), sbi = tbix(h * HALF, c);  // this thread's first row in the block's double / int arrays
-    const int nwvl = cst.nwvl;
-    for (int i = tid; i < EXP_TAB * EXP_REP; i += NT) s_exp[i] = a.exp_tab[i / EXP_REP];
-    const unsigned tab_lane = (unsigned)__cvta_generic_to_shared(s_exp + (lane & (EXP_REP - 1)));
-    const bool plk_smem = nwvl <= PLK_MAX;
-    if (plk_smem)
-        for (int i = tid; i < nwvl; i += NT) {
-            s_plk[i] = a.planck_c[i];
-            s_plk[PLK_MAX + i] = a.planck_k[i];
-        }
-    const unsigned mbar = (unsigned)__cvta_generic_to_shared(s_mbar);
-    const unsigned tb_addr = (unsigned)__cvta_generic_to_shared(tb);
-    unsigned char* const rows = s_rows + (size_t)warp * ROWBUF3;
-    const unsigned rows_addr = (unsigned)__cvta_generic_to_shared(rows);
-    if (tid == 0) {
-        mbar_init(mbar, 1);
-        const int u = (int)atomicAdd(a.counter, 1u);
-        s_next[0] = u;
-        s_next[1] = 1;
-        if (u < a.nunits) tma_load_1d(tb_addr, a.tile + (size_t)(u / a.nsplit) * TILE_BYTES, TILE_BYTES, mbar);
-    }
-    __syncthreads();
-    int unit = *s_next;
-    unsigned phase = 0;
-    // s_next[1]: units this CTA has taken from the counter (a.quota: it leaves its slot to waiting kernels after that many);
-    // kept in shared memory - thread 0 alone needs it, once per unit, and the kernel has no register to spare
-
-    // The 60 rows of wavelength w (three candidates per layer, 128 bytes each) into this warp's buffer: eight consecutive
-    // lanes copy the eight 16-byte pieces of one row, four rows per instruction - contiguous 128 bytes on the global side
-    // (4 x 4 sectors per LDGSTS instead of 32 lanes in 32 rows) and conflict-free on the shared side (with a lane per row the
-    // copies took 30 shared-memory wavefronts per instruction instead of 4: a third of the kernel's shared-memory traffic).
-    auto request_rows = [&](int w) {
-        __syncwarp();
-        const char* base = reinterpret_cast<const char*>(a.coef) + (size_t)w * ROWB3 + (lane & 7) * 16;
-        const unsigned dst0 = rows_addr + (lane & 7) * 16 + (lane >> 3) * ROWS3;
-        const int* ro = tbi + TBI_ROWOFF + (lane >> 3);
-        unsigned off[NCAND * NLAY / 4];  // the 15 row offsets first, then the 15 copies back to back
-#pragma unroll
-        for (int i = 0; i < NCAND * NLAY / 4; ++i) off[i] = (unsigned)ro[4 * i];
-#pragma unroll
-        for (int i = 0; i < NCAND * NLAY / 4; ++i) cp_async16(dst0 + 4 * i * ROWS3, base + off[i]);
-        cp_async_commit();
-    };
-    // K1 for owned layer j from the row at cf: the bilinear (p, T) interpolation of repwvl_thermal.cpp:235-246,
-    //   x = c0 + cT*dT + cP*dP + cPT*dT*dP,   tau = numDens * sum_k x_k * vmr_k,
-    // contracted to three FMAs per species on {c0 + cP*dP, cT, cPT} and dT, dT*dP (17 instead of 42 FP64 instructions per
-    // layer and wavelength; within a few ulp of the reference's operation order - the bit-exact form is rcm_build_tau's).
-    // Staged and global-memory variant evaluate the same expression on the same numbers: bit-identical.
-    auto tau_from = [&](int j, const double2* cf, double cl) -> double {
-        const int r = h * HALF + j;
-        const double dT = tb[TB_DELT + sb + j * C], dTdP = tb[TB_DTDP + sb + j * C];
-        double c[16];
-#pragma unroll
-        for (int q2 = 0; q2 < 8; ++q2) {
-            const double2 v = cf[q2];
-            c[2 * q2] = v.x;
-            c[2 * q2 + 1] = v.y;
-        }
-        double acc = 0.0;
-#pragma unroll
-        for (int k = 0; k < NACT; ++k) {
-            double v = fma(c[3 * k + 1], dT, c[3 * k]);
-            v = fma(c[3 * k + 2], dTdP, v);
-            acc = fma(v, tb[TB_VMR + k * TBD_LEN + sb + j * C], acc);
-        }
-        acc = acc * cst.numDens[r];
-        return fma(cst.cloud_w[r], cl, acc);  // main.cpp:270: + cl on the cloud layer, + 0 * cl (exact) elsewhere
-    };
-
-    const int tau_clamp_hi = __double2hiint(a.tau_clamp);  // clamp_hi: rcm_device_math.cuh
-    while (unit < a.nunits) {
-        const int tile = unit / a.nsplit, split = unit - tile * a.nsplit;
-        mbar_wait(mbar, phase);  // the tile block of this unit has landed
-        phase ^= 1u;
-        const bool staged = a.stage_rows && !tbi[TBI_OUTSIDE];
-        const int item0 = split * a.ipu, item1 = min(item0 + a.ipu, a.nitem);
-        double E1[HALF], E2[HALF], Eu20 = 0.0;
-#pragma unroll
-        for (int j = 0; j < HALF; ++j) E1[j] = E2[j] = 0.0;
-        if (staged) request_rows(min(g + item0 * G, nwvl - 1));
-#pragma unroll 1
-        for (int item = item0; item < item1; ++item) {
-            const int w_any = g + item * G;
-            const bool real = w_any < nwvl;  // a round beyond the table repeats the last wavelength with a zero source
-            const int w = real ? w_any : nwvl - 1;
-            double tau[HALF], Bo[HALF];
-            const double cl = tb[TB_CLOUD + c];
-            if (staged) {
-                cp_async_wait_all();
-                __syncwarp();
-#pragma unroll
-                for (int j = 0; j < HALF; ++j) {
-                    const double v = tau_from(j, reinterpret_cast<const double2*>(rows + tbi[TBI_ROWSEL + sbi + j * C]), cl);
-                    tau[j] = CLAMPK ? v : clamp_hi(v, tau_clamp_hi);
-                }
-                if (item + 1 < item1) request_rows(min(w_any + G, nwvl - 1));
-            } else {
-#pragma unroll
-                for (int j = 0; j < HALF; ++j) {
-                    const int cell = cst.ipcell[h * HALF + j] + tbi[TBI_IT + sbi + j * C];
-                    const double v = tau_from(j, reinterpret_cast<const double2*>(a.coef) + (size_t)(cell * nwvl + w) * 8, cl);
-                    tau[j] = fmax(CLAMPK ? v : clamp_hi(v, tau_clamp_hi), TAU_FLOOR);
-                }
-            }
-            // K2: Planck source B = k_w / (exp(c_w / T) - 1) (main.cpp:188-191, wavelength-only factors from the host)
-            const double pc = plk_smem ? s_plk[w] : __ldg(a.planck_c + w);
-            const double pk = !real ? 0.0 : plk_smem ? s_plk[PLK_MAX + w] : __ldg(a.planck_k + w);
-#pragma unroll
-            for (int j = 0; j < HALF; ++j)
-                Bo[j] = div_fast(pk, exp_scaled<false>(pc, tb[TB_INVT + sb + j * C], tab_lane) - 1.0);
-            const double Bs = div_fast(pk, exp_scaled<false>(pc, tb[TB_INVTS + c], tab_lane) - 1.0);
-            sweep_item<CLAMPK>(tau, Bo, Bs, h, tab_lane, E1, E2, Eu20);
-        }
-        // ---- K4: the four groups' partial fluxes through the row buffers, summed in group order -------------------
-        {
-            double* part = reinterpret_cast<double*>(s_rows + (size_t)g * ROWBUF3);
-#pragma unroll
-            for (int j = 0; j < HALF; ++j) {
-                const int l = h ? (NLAY - 1 - j) : j;
-                part[l * C + c] = h ? E2[j] : E1[j];
-                part[(NLEV + l) * C + c] = h ? E1[j] : E2[j];
-            }
-            if (h) part[(NLEV + NLAY) * C + c] = Eu20;
-        }
-        __syncthreads();  // nobody reads the tile block any more: the next unit's block may land
-        if (tid == 0) {
-            const int taken = s_next[1];
-            const int u = (taken < a.quota) ? (int)atomicAdd(a.counter, 1u) : a.nunits;
-            s_next[0] = u;
-            s_next[1] = taken + 1;
-            if (u < a.nunits) tma_load_1d(tb_addr, a.tile + (size_t)(u / a.nsplit) * TILE_BYTES, TILE_BYTES, mbar);
-        }
-        double* out = a.part + (size_t)unit * SPLIT_PART;
-        for (int i = tid; i < SPLIT_PART; i += NT) {
-            double sum = 0.0;
-            if (i / C != NLAY) {
-#pragma unroll
-                for (int gg = 0; gg < G; ++gg) sum += reinterpret_cast<const double*>(s_rows + (size_t)gg * ROWBUF3)[i];
-            }
-            out[i] = sum;
-        }
-        __syncthreads();  // row buffers free again; s_next visible
-        unit = *s_next;
-    }
+template <bool CLAMPK>
+__global__ void __launch_bounds__(SPLIT_NT, 3) rcm_split_multi_kernel(const __grid_constant__ SplitArgs a, const __grid_constant__ SplitMultiArgs m) {
+#define RCM_SPLIT_MULTI 1
+#include "rcm_split_unit_loop.inc"
+#undef RCM_SPLIT_MULTI
 }

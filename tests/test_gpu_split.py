@@ -185,3 +185,32 @@ def test_step_host_graph_path_is_bit_identical(rcm):
     assert s.launch_count() - l0 >= 6 * (3 * 8 + 1)               # graph launches count their kernels too
     assert s.host_graph_stats() == (2, 5)                         # captured at call 2 and call 6, replayed 5 times
     s.close()
+
+
+@pytest.mark.parametrize("ncol,n", [(333, 100), (5000, 100), (50, 20), (17, 10)])
+def test_multi_step_launch_is_bit_identical_to_three_launches_per_step(rcm, ncol, n):
+    """rcm_advance(k >= 2) as ONE persistent launch (per-tile step flags, the K5 body run by the CTA that completes a tile's
+    step; option 6 = 2 forces it) against a K5 / unit / K5 launch sequence per step (option 6 = 0): every output and every
+    step's ensemble scalars, over blocks of different lengths - and against single steps."""
+    st = ensemble(rcm, ncol, 77 + n, n)
+    s = rcm.Solver(0)
+    s.set_repwvl_table_from(rcm.Table(table_path(n)))
+    out = {}
+    for multi in (2, 0):
+        s.set_option(6, multi)
+        s.set_columns(st["plevel"], st["Tlayer"], st["Tsurf"], st["vmr9"], st["rel_hum"])
+        l0 = s.launch_count()
+        sc = [s.advance(k) for k in (2, 7, 1, 40)]
+        launches = s.launch_count() - l0
+        out[multi] = (s.get_state(), np.concatenate(sc))
+        # one launch per block: K5 prep + unit kernel + scalar reduction per call (the single step: prep, unit, finish, reduction)
+        # (+ the two table kernels after the first rcm_set_columns)
+        assert (launches <= 3 * 3 + 4 + 2) if multi else (launches >= 4 * 1 + 2 * 50 + 4), (multi, launches)
+    s.set_option(6, 0)
+    single = run(s, st, slice(None), (1,) * 50)
+    s.close()
+    for k in KEYS:
+        assert np.array_equal(out[2][0][k], out[0][0][k]), k
+        assert np.array_equal(out[2][0][k], single[0][k]), k
+    assert np.array_equal(out[2][1], out[0][1]) and np.array_equal(out[2][1], single[1])
+    assert np.isfinite(out[2][1]).all() and out[2][1].shape == (50, 4)
