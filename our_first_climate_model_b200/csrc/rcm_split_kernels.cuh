@@ -17,10 +17,13 @@
 //       prep of step n+1  : theta-sort, stationarity diagnostic, water-vapour feedback, table indices and
 //                           interpolation weights in T, 1/T, row-staging plan                (main.cpp:536-540, :281-289,
 //                                                                                            repwvl_thermal.cpp:226-240)
-//       and leaves everything the unit kernel needs for the tile in ONE contiguous 20,992-byte block.
+//       and leaves everything the unit kernel needs for the tile in ONE contiguous 24,192-byte block.
 //   rcm_split_rt_kernel   K1-K4 for (tile, split) units: the tile block arrives by ONE TMA bulk copy
 //       (cp.async.bulk + mbarrier), issued for the NEXT unit while the partial fluxes of the current one are reduced;
 //       K1 rows are staged per warp by cp.async as in the fused kernel; partial fluxes leave as [42][16] per unit.
+//   rcm_split_multi_kernel  the same unit code (rcm_split_unit_loop.inc) for a BLOCK of steps in one launch: (step, unit)
+//       items, per-tile step flags instead of kernel boundaries, the K5 body run in place by the CTA that completes a
+//       tile's step.  For small shards, where a step is only a few rounds per CTA (see the comment in front of it).
 #pragma once
 
 constexpr int SPLIT_C = 16, SPLIT_NT = 128, SPLIT_G = 4;
