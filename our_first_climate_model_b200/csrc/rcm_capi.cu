@@ -621,7 +621,9 @@ int split_advance(rcm_solver* s, int nsteps) {
     static const int multi_rounds = std::getenv("RCM_MULTI_ROUNDS") ? std::atoi(std::getenv("RCM_MULTI_ROUNDS")) : 24;
     const int grid1 = split_grid(s, a, nsm);
     const bool few_rounds = a.nunits < (long long)multi_rounds * grid1;
-    if (nsteps >= 2 && (s->opt_multi == 2 || (s->opt_multi == 1 && few_rounds))) {
+    // (item numbers are 32-bit: units x steps of one launch, plus the tickets of the CTAs that find the counter exhausted)
+    const bool fits = (long long)a.nunits * nsteps + 2LL * grid1 < (1LL << 31);
+    if (nsteps >= 2 && fits && (s->opt_multi == 2 || (s->opt_multi == 1 && few_rounds))) {
         // a block of steps as ONE launch: (step, unit) items in step-major order, per-tile step flags instead of kernel
         // boundaries, the K5 body run by the CTA that completes a tile's step (rcm_split_multi_kernel)
         SplitMultiArgs m{};
