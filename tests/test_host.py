@@ -304,3 +304,53 @@ def test_clock_sampler_evaluates_only_the_timed_window():
     c = s.stop()
     assert c["samples"] == 4 and c["gpus_sampled"] == 2 and c["reasons"] == ["sw_power_cap"]
     assert c["sm_max_mhz"] == 1965.0 and c["per_gpu_sm_mhz"] == {"min": 1942.5, "max": 1965.0}
+
+
+def test_multi_step_protocol_model():
+    """A host-side model of rcm_split_multi_kernel's scheduling (rcm_split_unit_loop.inc, RCM_SPLIT_MULTI): items = (step, unit) in
+    step-major order from one counter, a unit of step n may start when ready[tile] >= n, the CTA that completes a tile's last
+    unit of a step runs the tile's finish / prep and publishes ready[tile] = n + 1.  Under random interleavings of any number
+    of CTAs - fewer than items, more than items, one - every item completes (dependencies point to lower item numbers only),
+    each (tile, step) is finished exactly once, after all of its units and before any unit of the next step."""
+    import random
+    rng = random.Random(5)
+    for ntiles, nsplit, nsteps, nctas in [(7, 5, 6, 4), (3, 5, 4, 40), (16, 1, 5, 9), (5, 2, 9, 1), (32, 5, 3, 13)]:
+        nunits = ntiles * nsplit
+        total = nunits * nsteps
+        counter, done, ready = 0, [0] * ntiles, [0] * ntiles
+        log = []                                            # ("unit", tile, step) / ("k5", tile, step) in completion order
+        state = [("take", None)] * nctas                    # per CTA: take an item / wait for its flag / work / exited
+        exited = 0
+        for _ in range(200 * total + 1000):
+            if exited == nctas:
+                break
+            c = rng.randrange(nctas)
+            kind, item = state[c]
+            if kind == "take":
+                item, counter = counter, counter + 1
+                state[c] = ("exit", None) if item >= total else ("wait", item)
+            elif kind == "wait":
+                step, tile = item // nunits, (item % nunits) // nsplit
+                if ready[tile] >= step:
+                    state[c] = ("work", item)
+            elif kind == "work":
+                step, tile = item // nunits, (item % nunits) // nsplit
+                log.append(("unit", tile, step))
+                done[tile] += 1
+                if done[tile] % nsplit == 0:               # this CTA finished the tile's step: K5 body in place, then publish
+                    log.append(("k5", tile, step))
+                    ready[tile] = step + 1
+                state[c] = ("take", None)
+            elif kind == "exit":
+                state[c] = ("gone", None)
+                exited += 1
+        assert exited == nctas, "the model deadlocked"
+        assert sum(1 for e in log if e[0] == "unit") == total
+        pos = {e: i for i, e in enumerate(log)}
+        for tile in range(ntiles):
+            for step in range(nsteps):
+                k5 = pos[("k5", tile, step)]
+                units = [i for i, e in enumerate(log) if e == ("unit", tile, step)]
+                assert len(units) == nsplit and max(units) < k5
+                if step + 1 < nsteps:
+                    assert k5 < min(i for i, e in enumerate(log) if e == ("unit", tile, step + 1))
